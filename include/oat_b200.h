@@ -1,0 +1,132 @@
+/*
+ * oat_b200.h — C-ABI of the B200-native OATomobile RIP/DIM hot path.
+ *
+ * The reference (OATML/oatomobile) has no FFI: its boundary for this path is
+ * the Python class API of `oatomobile/baselines/torch/__init__.py:17-21`.
+ * Every entry point below names the reference function it replaces
+ * (paths relative to the reference root).  `oatomobile_b200/` binds these
+ * with ctypes and re-exposes the reference's Python classes on top; the
+ * binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; every tensor argument is a *device* pointer to
+ *    contiguous float32 unless its name starts with `h_` (host pointer);
+ *  - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream);
+ *  - every function returns 0 on success, non-zero on failure;
+ *    `oat_last_error()` then returns a thread-local message;
+ *  - kernels are enqueued on `stream` and NOT synchronised;
+ *  - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef OAT_B200_H_
+#define OAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define OAT_API __attribute__((visibility("default")))
+#else
+#define OAT_API
+#endif
+
+#define OAT_ABI_VERSION 1
+#define OAT_HIDDEN 64        /* GRU hidden size (sequence.py:36, dim/model.py:67) */
+#define OAT_ENC_FEATURES 128 /* encoder output width (dim/model.py:53)            */
+
+/* A named host tensor: one entry of a reference `state_dict()`.            */
+typedef struct OatTensor {
+  const char* name;  /* e.g. "_encoder._model.features.0.0.weight"          */
+  const void* h_data; /* host pointer, float32 (int64 entries are ignored)   */
+  int32_t ndim;
+  int64_t shape[4];
+} OatTensor;
+
+typedef struct OatModel OatModel;       /* one ImitativeModel / BehaviouralModel */
+typedef struct OatEnsemble OatEnsemble; /* E models on one GPU + workspace       */
+
+enum { OAT_KIND_DIM = 0, OAT_KIND_CIL = 1, OAT_KIND_FLOW = 2 /* AutoregressiveFlow alone */ };
+enum { OAT_ALGO_WCM = 0, OAT_ALGO_BCM = 1, OAT_ALGO_MA = 2 };
+
+OAT_API const char* oat_last_error(void);
+OAT_API int oat_abi_version(void);
+
+/* Replaces `ImitativeModel.__init__ + load_state_dict` (dim/model.py:39-68) and
+ * `BehaviouralModel.__init__` (cil/model.py:34-66) on the device side: takes the
+ * reference state_dict (328 / 326 entries), folds the 52 eval-mode BatchNorms
+ * into their convolutions, re-lays the weights out for the kernels and uploads
+ * them to `device`.  `in_channels` is read from the stem's shape.  With
+ * OAT_KIND_FLOW only the decoder is packed, from the keys of a stand-alone
+ * `AutoregressiveFlow` (`_decoder.weight_ih`, `_locscale._model.0.weight`, ...;
+ * oatomobile/torch/networks/sequence.py:53-65).                                  */
+OAT_API int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind,
+                     int32_t device, OatModel** out);
+OAT_API int oat_model_destroy(OatModel* model);
+OAT_API int oat_model_in_channels(const OatModel* model);
+
+/* Groups E models that live on this GPU (RIPAgent.__init__, rip/agent.py:49-50).
+ * Owns the activation workspace, grown on demand by `oat_ensemble_reserve`
+ * (called implicitly by oat_encode). */
+OAT_API int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble** out);
+OAT_API int oat_ensemble_destroy(OatEnsemble* ens);
+OAT_API int oat_ensemble_reserve(OatEnsemble* ens, int32_t batch);
+
+/* transforms.downsample_visual_features + transpose_visual_features
+ * (oatomobile/torch/transforms.py:34-49, called from dim/model.py:245-251):
+ * lidar [B,C,H,W] -> visual [B,C,100,100], bilinear align_corners=True then H<->W. */
+OAT_API int oat_transform_visual(const float* lidar, int32_t B, int32_t C, int32_t H, int32_t W,
+                         float* visual, void* stream);
+
+/* `ImitativeModel._params` (dim/model.py:173-219) for every model of the ensemble:
+ * visual [B,C,100,100] (shared), scalars [B,S] = cat(velocity(3), is_at_traffic_light(1),
+ * traffic_light_state(1) [, mode(1) for CIL]) -> z [E,B,64].                      */
+OAT_API int oat_encode(OatEnsemble* ens, const float* visual, const float* scalars,
+               int32_t B, float* z, void* stream);
+
+/* `AutoregressiveFlow._forward` (oatomobile/torch/networks/sequence.py:95-151):
+ * x [N,T,2], z [N/rows_per_z,64] -> y [N,T,2], logabsdet [N] (may be NULL).
+ * Row n uses z[n / rows_per_z] (rows_per_z = 1 reproduces the reference call). */
+OAT_API int oat_flow_forward(const OatModel* model, const float* x, const float* z,
+                     int64_t N, int32_t T, int32_t rows_per_z,
+                     float* y, float* logabsdet, void* stream);
+
+/* `AutoregressiveFlow._inverse` (sequence.py:153-216): y [N,T,2] ->
+ * x [N,T,2] (may be NULL), log_prob [N], logabsdet [N].                          */
+OAT_API int oat_flow_inverse(const OatModel* model, const float* y, const float* z,
+                     int64_t N, int32_t T, int32_t rows_per_z,
+                     float* x, float* log_prob, float* logabsdet, void* stream);
+
+/* K-sample sample-and-score (BASELINE.json metric; SURVEY.md 3.5, assembled from
+ * rip/agent.py:106-119,137): proposals y = f_p(x; z_p) from local model
+ * `proposal_idx` (pass -1 when `y` is an INPUT produced elsewhere, e.g. by the
+ * rank that owns model 0), then q[m,b,k] = log_prob_m - logabsdet_m
+ * (+ per-sample goal log-likelihood, dim/model.py:143-171, when goal != NULL).
+ * z [E,B,64], x [B,K,T,2], goal [B,G,2] or NULL, y [B,K,T,2], q [E,B,K].        */
+OAT_API int oat_rip_sample_score(OatEnsemble* ens, int32_t proposal_idx, const float* z,
+                         const float* x, const float* goal, int32_t G, float epsilon,
+                         int32_t B, int32_t K, int32_t T,
+                         float* y, float* q, void* stream);
+
+/* Ensemble aggregation + plan selection (rip/agent.py:121-127,137):
+ * s[b,k] = min_m(-q) ("WCM") | max_m(-q) ("BCM") | mean_m(-q) ("MA") as written in
+ * the reference; kstar[b] = argmin_k s (lowest k on ties); plan[b] = y[b,kstar[b]].
+ * q [E,B,K]; s [B,K] (may be NULL); kstar int32 [B]; sbest [B]; plan [B,T,2].    */
+OAT_API int oat_rip_aggregate(const float* q, int32_t E, int32_t B, int32_t K, int32_t algo,
+                      const float* y, int32_t T, float* s, int32_t* kstar,
+                      float* sbest, float* plan, void* stream);
+
+/* `BehaviouralModel.forward` roll-out (cil/model.py:106-127) after the encoder:
+ * z [B,64] -> y [B,T,2].                                                          */
+OAT_API int oat_cil_rollout(const OatModel* model, const float* z, int32_t B, int32_t T,
+                    float* y, void* stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's
+ * `gpu_launches`). */
+OAT_API int64_t oat_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OAT_B200_H_ */

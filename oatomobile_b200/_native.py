@@ -1,0 +1,174 @@
+"""ctypes binding of `liboat_b200.so` (the C-ABI declared in include/oat_b200.h).
+
+The library is the product: there is no PyTorch/CPU fallback.  If the shared
+object is missing, or no CUDA device is present, every entry point raises.
+"""
+import ctypes
+import os
+import threading
+from typing import Dict, Mapping, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboat_b200.so")
+
+KIND_DIM, KIND_CIL, KIND_FLOW = 0, 1, 2
+ALGORITHMS = {"WCM": 0, "BCM": 1, "MA": 2}
+
+# Every symbol include/oat_b200.h declares (checked by tests/test_abi.py).
+SYMBOLS = (
+    "oat_last_error", "oat_abi_version", "oat_model_create", "oat_model_destroy",
+    "oat_model_in_channels", "oat_ensemble_create", "oat_ensemble_destroy",
+    "oat_ensemble_reserve", "oat_transform_visual", "oat_encode", "oat_flow_forward",
+    "oat_flow_inverse", "oat_rip_sample_score", "oat_rip_aggregate", "oat_cil_rollout",
+    "oat_launch_count",
+)
+
+
+class NativeLibraryError(RuntimeError):
+  """The CUDA library is missing or a native call failed."""
+
+
+class OatTensor(ctypes.Structure):
+  _fields_ = [("name", ctypes.c_char_p), ("h_data", ctypes.c_void_p),
+              ("ndim", ctypes.c_int32), ("shape", ctypes.c_int64 * 4)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> ctypes.CDLL:
+  """Loads the in-tree shared object; raises loudly when it is absent."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  with _lock:
+    if _lib is not None:
+      return _lib
+    if not os.path.exists(LIB_PATH):
+      raise NativeLibraryError(
+          "oatomobile_b200: %s not found. Build it with `python -m oatomobile_b200.build` "
+          "(nvcc, sm_100a). There is no CPU/PyTorch fallback for this path." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    c_int, c_i32, c_i64, c_f, vp = (ctypes.c_int, ctypes.c_int32, ctypes.c_int64,
+                                    ctypes.c_float, ctypes.c_void_p)
+    L.oat_last_error.restype = ctypes.c_char_p
+    L.oat_abi_version.restype = c_int
+    L.oat_launch_count.restype = c_i64
+    L.oat_model_create.argtypes = [ctypes.POINTER(OatTensor), c_i32, c_i32, c_i32,
+                                   ctypes.POINTER(vp)]
+    L.oat_model_destroy.argtypes = [vp]
+    L.oat_model_in_channels.argtypes = [vp]
+    L.oat_ensemble_create.argtypes = [ctypes.POINTER(vp), c_i32, ctypes.POINTER(vp)]
+    L.oat_ensemble_destroy.argtypes = [vp]
+    L.oat_ensemble_reserve.argtypes = [vp, c_i32]
+    L.oat_transform_visual.argtypes = [vp, c_i32, c_i32, c_i32, c_i32, vp, vp]
+    L.oat_encode.argtypes = [vp, vp, vp, c_i32, vp, vp]
+    L.oat_flow_forward.argtypes = [vp, vp, vp, c_i64, c_i32, c_i32, vp, vp, vp]
+    L.oat_flow_inverse.argtypes = [vp, vp, vp, c_i64, c_i32, c_i32, vp, vp, vp, vp]
+    L.oat_rip_sample_score.argtypes = [vp, c_i32, vp, vp, vp, c_i32, c_f, c_i32, c_i32, c_i32,
+                                       vp, vp, vp]
+    L.oat_rip_aggregate.argtypes = [vp, c_i32, c_i32, c_i32, c_i32, vp, c_i32, vp, vp, vp, vp,
+                                    vp]
+    L.oat_cil_rollout.argtypes = [vp, vp, c_i32, c_i32, vp, vp]
+    for name in SYMBOLS:
+      fn = getattr(L, name, None)
+      if fn is not None and name not in ("oat_last_error", "oat_launch_count"):
+        fn.restype = c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+  if rc != 0:
+    raise NativeLibraryError(lib().oat_last_error().decode() or "native call failed")
+
+
+def launch_count() -> int:
+  return int(lib().oat_launch_count())
+
+
+def stream_ptr(device: torch.device) -> int:
+  return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+  return None if t is None else t.data_ptr()
+
+
+def require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+  """The kernels read contiguous float32 device memory; anything else is an error
+  (CPU tensors in particular: this path has no CPU implementation)."""
+  if not isinstance(t, torch.Tensor):
+    raise TypeError("`%s` must be a torch.Tensor" % name)
+  if not t.is_cuda:
+    raise NativeLibraryError(
+        "`%s` lives on %s: oatomobile_b200 runs on CUDA (sm_100a) only, there is no CPU "
+        "fallback. Move the model and its inputs to a GPU." % (name, t.device))
+  if t.dtype != torch.float32:
+    t = t.float()
+  return t.contiguous()
+
+
+class ModelHandle:
+  """Owns one `OatModel*` built from a reference-format state_dict."""
+
+  def __init__(self, state_dict: Mapping[str, torch.Tensor], kind: int, device: torch.device):
+    L = lib()
+    if device.type != "cuda":
+      raise NativeLibraryError("oatomobile_b200 models run on CUDA devices only (got %s)" % device)
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    keep, arr = [], []
+    for name, t in state_dict.items():
+      if not torch.is_floating_point(t):
+        continue  # num_batches_tracked (int64) is unused in eval mode
+      h = t.detach().to("cpu", torch.float32).contiguous()
+      keep.append(h)
+      shape = (ctypes.c_int64 * 4)(*(list(h.shape) + [0] * (4 - h.dim())))
+      arr.append(OatTensor(name.encode(), h.data_ptr(), h.dim(), shape))
+    c_arr = (OatTensor * len(arr))(*arr)
+    out = ctypes.c_void_p()
+    check(L.oat_model_create(c_arr, len(arr), kind, index, ctypes.byref(out)))
+    self.ptr = out
+    self.kind = kind
+    self.device = torch.device("cuda", index)
+
+  def __deepcopy__(self, memo):  # device handles are never shared between copies
+    return None
+
+  def __del__(self):
+    try:
+      if getattr(self, "ptr", None):
+        lib().oat_model_destroy(self.ptr)
+        self.ptr = None
+    except Exception:
+      pass
+
+
+class EnsembleHandle:
+  """Owns one `OatEnsemble*` over E model handles living on the same GPU."""
+
+  def __init__(self, models: Sequence[ModelHandle]):
+    L = lib()
+    self.models = list(models)  # keep the model handles alive
+    arr = (ctypes.c_void_p * len(models))(*[m.ptr.value for m in models])
+    out = ctypes.c_void_p()
+    check(L.oat_ensemble_create(arr, len(models), ctypes.byref(out)))
+    self.ptr = out
+    self.device = models[0].device
+
+  def __len__(self):
+    return len(self.models)
+
+  def __deepcopy__(self, memo):
+    return None
+
+  def __del__(self):
+    try:
+      if getattr(self, "ptr", None):
+        lib().oat_ensemble_destroy(self.ptr)
+        self.ptr = None
+    except Exception:
+      pass

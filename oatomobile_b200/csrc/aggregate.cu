@@ -1,0 +1,82 @@
+// Ensemble aggregation + plan selection (sm_100a).
+//
+// Replaces oatomobile/baselines/torch/rip/agent.py:121-127 (stack -> min/max/mean
+// over models) and the plan decode of :137 for the K-sample formulation:
+//   s[b,k] = min_m(-q) | max_m(-q) | mean_m(-q);  k* = argmin_k s;  plan = y[b,k*].
+// HBM-bound: reads E*4 bytes per sample once (coalesced along k), writes 4 (s).
+// One CTA per scene b; warp-shuffle (value,index) reduction, lowest index on ties
+// like torch.argmin; MA sums models in index order 0..E-1 then divides by E so
+// every rank of a sharded ensemble reproduces the same bits.
+#include "common.cuh"
+
+namespace oat {
+namespace {
+
+constexpr int ATHREADS = 256;
+
+__device__ __forceinline__ void argmin_combine(float& v, int& k, float v2, int k2) {
+  if (v2 < v || (v2 == v && k2 < k)) { v = v2; k = k2; }
+}
+
+__global__ void __launch_bounds__(ATHREADS) aggregate_kernel(
+    const float* __restrict__ q, int E, int B, int K, int algo, const float* __restrict__ y,
+    int T, float* __restrict__ s, int32_t* __restrict__ kstar, float* __restrict__ sbest,
+    float* __restrict__ plan) {
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int64_t BK = (int64_t)B * K;
+  const float* qb = q + (int64_t)b * K;
+  float best = INFINITY;
+  int bestk = 0x7fffffff;
+  for (int k = tid; k < K; k += ATHREADS) {
+    float v = -__ldg(qb + k);
+    if (algo == OAT_ALGO_WCM) {
+      for (int m = 1; m < E; ++m) v = fminf(v, -__ldg(qb + m * BK + k));
+    } else if (algo == OAT_ALGO_BCM) {
+      for (int m = 1; m < E; ++m) v = fmaxf(v, -__ldg(qb + m * BK + k));
+    } else {
+      for (int m = 1; m < E; ++m) v = v + (-__ldg(qb + m * BK + k));
+      v = v / (float)E;
+    }
+    if (s != nullptr) s[(int64_t)b * K + k] = v;
+    if (v < best) { best = v; bestk = k; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float v2 = __shfl_xor_sync(0xffffffffu, best, off);
+    const int k2 = __shfl_xor_sync(0xffffffffu, bestk, off);
+    argmin_combine(best, bestk, v2, k2);
+  }
+  __shared__ float sv[ATHREADS / 32];
+  __shared__ int sk[ATHREADS / 32];
+  __shared__ int kfinal;
+  if ((tid & 31) == 0) { sv[tid >> 5] = best; sk[tid >> 5] = bestk; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < ATHREADS / 32; ++w) argmin_combine(best, bestk, sv[w], sk[w]);
+    if (bestk == 0x7fffffff) bestk = 0;  // all-NaN / empty row
+    kfinal = bestk;
+    kstar[b] = bestk;
+    if (sbest != nullptr) sbest[b] = best;
+  }
+  __syncthreads();
+  if (plan != nullptr && y != nullptr) {
+    const float* src = y + ((int64_t)b * K + kfinal) * (2 * T);
+    for (int i = tid; i < 2 * T; i += ATHREADS) plan[(int64_t)b * 2 * T + i] = __ldg(src + i);
+  }
+}
+
+}  // namespace
+
+int launch_aggregate(const float* q, int E, int B, int K, int algo, const float* y, int T,
+                     float* s, int32_t* kstar, float* sbest, float* plan,
+                     cudaStream_t stream) {
+  if (B <= 0) return 0;
+  if (E < 1 || K < 1) return fail("aggregate: need E >= 1 and K >= 1");
+  if (algo < OAT_ALGO_WCM || algo > OAT_ALGO_MA) return fail("aggregate: unknown algorithm");
+  aggregate_kernel<<<B, ATHREADS, 0, stream>>>(q, E, B, K, algo, y, T, s, kstar, sbest, plan);
+  OAT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace oat

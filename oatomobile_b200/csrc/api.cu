@@ -1,0 +1,486 @@
+// C-ABI entry points (include/oat_b200.h) and weight packing.
+//
+// `oat_model_create` consumes the reference `state_dict` verbatim (key names of
+// oatomobile/baselines/torch/dim/model.py:53-68 + torchvision MobileNetV2),
+// folds each eval-mode BatchNorm into the convolution in front of it (in double
+// precision), transposes every matrix into the K-major layout the kernels read
+// and uploads one arena per model.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace oat {
+
+static thread_local std::string g_error;
+int64_t g_launch_count = 0;
+
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(const std::string& msg) {
+  g_error = msg;
+  return 1;
+}
+
+namespace {
+
+struct HostTensor {
+  const float* data;
+  std::vector<int64_t> shape;
+};
+
+struct Packer {
+  std::map<std::string, HostTensor> sd;
+  std::vector<float> arena;
+  std::string err;
+
+  const HostTensor* get(const std::string& name, std::initializer_list<int64_t> shape = {}) {
+    auto it = sd.find(name);
+    if (it == sd.end()) {
+      if (err.empty()) err = "state_dict is missing `" + name + "`";
+      return nullptr;
+    }
+    if (shape.size() != 0) {
+      std::vector<int64_t> want(shape);
+      if (it->second.shape != want) {
+        if (err.empty()) err = "state_dict entry `" + name + "` has an unexpected shape";
+        return nullptr;
+      }
+    }
+    return &it->second;
+  }
+  size_t alloc(size_t n) {  // 128-byte aligned sub-allocation
+    size_t off = (arena.size() + 31) & ~size_t(31);
+    arena.resize(off + n, 0.0f);
+    return off;
+  }
+  // Folded BN: scale = gamma / sqrt(var + eps), shift = beta - mean * scale.
+  bool bn(const std::string& p, int64_t n, std::vector<double>* scale, std::vector<double>* shift) {
+    const HostTensor *g = get(p + ".weight", {n}), *b = get(p + ".bias", {n}),
+                     *m = get(p + ".running_mean", {n}), *v = get(p + ".running_var", {n});
+    if (!g || !b || !m || !v) return false;
+    scale->resize(n);
+    shift->resize(n);
+    for (int64_t i = 0; i < n; ++i) {
+      const double s = (double)g->data[i] / std::sqrt((double)v->data[i] + 1e-5);
+      (*scale)[i] = s;
+      (*shift)[i] = (double)b->data[i] - (double)m->data[i] * s;
+    }
+    return true;
+  }
+};
+
+struct Off {
+  size_t w, b;
+};
+
+// 1x1 conv [N,K,1,1] + BN -> w[K][N], b[N]
+bool pack_pw(Packer& P, const std::string& conv, const std::string& bnp, int64_t K, int64_t N,
+             Off* o) {
+  const HostTensor* w = P.get(conv + ".weight", {N, K, 1, 1});
+  std::vector<double> sc, sh;
+  if (!w || !P.bn(bnp, N, &sc, &sh)) return false;
+  o->w = P.alloc(K * N);
+  o->b = P.alloc(N);
+  for (int64_t n = 0; n < N; ++n) {
+    for (int64_t k = 0; k < K; ++k) P.arena[o->w + k * N + n] = (float)((double)w->data[n * K + k] * sc[n]);
+    P.arena[o->b + n] = (float)sh[n];
+  }
+  return true;
+}
+
+// depthwise 3x3 [C,1,3,3] + BN -> w[9][C], b[C]
+bool pack_dw(Packer& P, const std::string& conv, const std::string& bnp, int64_t C, Off* o) {
+  const HostTensor* w = P.get(conv + ".weight", {C, 1, 3, 3});
+  std::vector<double> sc, sh;
+  if (!w || !P.bn(bnp, C, &sc, &sh)) return false;
+  o->w = P.alloc(9 * C);
+  o->b = P.alloc(C);
+  for (int64_t c = 0; c < C; ++c) {
+    for (int t = 0; t < 9; ++t) P.arena[o->w + t * C + c] = (float)((double)w->data[c * 9 + t] * sc[c]);
+    P.arena[o->b + c] = (float)sh[c];
+  }
+  return true;
+}
+
+// Linear [N,K] (+bias) -> w[K][N], b[N]
+bool pack_linear(Packer& P, const std::string& p, int64_t K, int64_t N, Off* o) {
+  const HostTensor *w = P.get(p + ".weight", {N, K}), *b = P.get(p + ".bias", {N});
+  if (!w || !b) return false;
+  o->w = P.alloc(K * N);
+  o->b = P.alloc(N);
+  for (int64_t n = 0; n < N; ++n) {
+    for (int64_t k = 0; k < K; ++k) P.arena[o->w + k * N + n] = w->data[n * K + k];
+    P.arena[o->b + n] = b->data[n];
+  }
+  return true;
+}
+
+// (expand t, out c, repeats n, first stride s) — Sandler et al. 2018, table 2.
+const int kSetting[7][4] = {{1, 16, 1, 1}, {6, 24, 2, 2},  {6, 32, 3, 2}, {6, 64, 4, 2},
+                            {6, 96, 3, 1}, {6, 160, 3, 2}, {6, 320, 1, 1}};
+
+}  // namespace
+}  // namespace oat
+
+using namespace oat;
+
+extern "C" {
+
+const char* oat_last_error(void) { return g_error.c_str(); }
+int oat_abi_version(void) { return OAT_ABI_VERSION; }
+int64_t oat_launch_count(void) { return g_launch_count; }
+
+int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind, int32_t device,
+                     OatModel** out) {
+  if (!tensors || !out) return fail("oat_model_create: null argument");
+  if (kind != OAT_KIND_DIM && kind != OAT_KIND_CIL && kind != OAT_KIND_FLOW)
+    return fail("oat_model_create: bad kind");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("oat_model_create: no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("oat_model_create: bad device index");
+
+  Packer P;
+  for (int i = 0; i < num_tensors; ++i) {
+    const OatTensor& t = tensors[i];
+    if (!t.name || !t.h_data) continue;
+    HostTensor h;
+    h.data = static_cast<const float*>(t.h_data);
+    for (int d = 0; d < t.ndim && d < 4; ++d) h.shape.push_back(t.shape[d]);
+    P.sd[t.name] = h;
+  }
+  const std::string enc = "_encoder._model.";
+  const std::string f = enc + "features.";
+
+  // ---- stem: features.0 = conv3x3 s2 (C->32) + BN + ReLU6 (perception.py:43-51)
+  const bool has_encoder = kind != OAT_KIND_FLOW;
+  auto stem_it = P.sd.find(f + "0.0.weight");
+  if (has_encoder && (stem_it == P.sd.end() || stem_it->second.shape.size() != 4))
+    return fail("state_dict is missing `" + f + "0.0.weight`");
+  const int64_t C = has_encoder ? stem_it->second.shape[1] : 0;
+  if (has_encoder && (stem_it->second.shape != std::vector<int64_t>({32, C, 3, 3}) || C < 1 || C > 8))
+    return fail("stem conv must be [32,C,3,3] with 1 <= C <= 8");
+  Off stem{0, 0};
+  if (has_encoder) {
+    std::vector<double> sc, sh;
+    if (!P.bn(f + "0.1", 32, &sc, &sh)) return fail(P.err);
+    const float* w = stem_it->second.data;
+    stem.w = P.alloc(9 * C * 32);
+    stem.b = P.alloc(32);
+    for (int64_t co = 0; co < 32; ++co) {
+      for (int64_t c = 0; c < C; ++c)
+        for (int t = 0; t < 9; ++t)
+          P.arena[stem.w + (t * C + c) * 32 + co] = (float)((double)w[(co * C + c) * 9 + t] * sc[co]);
+      P.arena[stem.b + co] = (float)sh[co];
+    }
+  }
+
+  // ---- 17 inverted-residual blocks
+  struct BlockOff {
+    int cin, hid, cout, stride, residual, hin, hout;
+    Off expand, dw, project;
+  };
+  std::vector<BlockOff> blocks;
+  if (has_encoder) {
+    int cin = 32, idx = 1, h = 50;
+    for (int s = 0; s < 7; ++s) {
+      for (int i = 0; i < kSetting[s][2]; ++i, ++idx) {
+        BlockOff b;
+        b.cin = cin;
+        b.hid = cin * kSetting[s][0];
+        b.cout = kSetting[s][1];
+        b.stride = (i == 0) ? kSetting[s][3] : 1;
+        b.residual = (b.stride == 1 && b.cin == b.cout) ? 1 : 0;
+        b.hin = h;
+        b.hout = (h - 1) / b.stride + 1;  // k=3, pad=1
+        const std::string p = f + std::to_string(idx) + ".conv";
+        bool ok = true;
+        if (b.hid != b.cin) {
+          ok = ok && pack_pw(P, p + ".0.0", p + ".0.1", b.cin, b.hid, &b.expand);
+          ok = ok && pack_dw(P, p + ".1.0", p + ".1.1", b.hid, &b.dw);
+          ok = ok && pack_pw(P, p + ".2", p + ".3", b.hid, b.cout, &b.project);
+        } else {
+          b.expand = Off{0, 0};
+          ok = ok && pack_dw(P, p + ".0.0", p + ".0.1", b.hid, &b.dw);
+          ok = ok && pack_pw(P, p + ".1", p + ".2", b.hid, b.cout, &b.project);
+        }
+        if (!ok) return fail(P.err);
+        blocks.push_back(b);
+        cin = b.cout;
+        h = b.hout;
+      }
+    }
+  }
+  Off last{0, 0}, fc{0, 0}, mg[3] = {{0, 0}, {0, 0}, {0, 0}}, flow{0, 0};
+  const int S = (kind == OAT_KIND_CIL) ? 6 : 5;
+  if (has_encoder) {
+    if (!pack_pw(P, f + "18.0", f + "18.1", 320, 1280, &last)) return fail(P.err);
+    if (!pack_linear(P, enc + "classifier.1", 1280, OAT_ENC_FEATURES, &fc)) return fail(P.err);
+    if (!pack_linear(P, "_merger._model.0", OAT_ENC_FEATURES + S, 64, &mg[0])) return fail(P.err);
+    if (!pack_linear(P, "_merger._model.2", 64, 64, &mg[1])) return fail(P.err);
+    if (!pack_linear(P, "_merger._model.4", 64, 64, &mg[2])) return fail(P.err);
+  }
+
+  // ---- GRU + head (sequence.py:53-65) / CIL GRU + output (cil/model.py:60-66)
+  {
+    const std::string g = (kind == OAT_KIND_DIM) ? "_decoder._decoder." : "_decoder.";  // FLOW == CIL key
+    const HostTensor *wih = P.get(g + "weight_ih", {192, 2}), *whh = P.get(g + "weight_hh", {192, 64}),
+                     *bih = P.get(g + "bias_ih", {192}), *bhh = P.get(g + "bias_hh", {192});
+    if (!wih || !whh || !bih || !bhh) return fail(P.err);
+    flow.w = P.alloc(kFlowFloats);
+    float* fw = nullptr;
+    auto F = [&]() { return P.arena.data() + flow.w; };
+    fw = F();
+    for (int j = 0; j < 192; ++j) {
+      for (int k = 0; k < 64; ++k) fw[kFlowWhh + k * 192 + j] = whh->data[j * 64 + k];
+      fw[kFlowWihT + j] = wih->data[j * 2 + 0];
+      fw[kFlowWihT + 192 + j] = wih->data[j * 2 + 1];
+      fw[kFlowBih + j] = bih->data[j];
+      fw[kFlowBhh + j] = bhh->data[j];
+    }
+    if (kind != OAT_KIND_CIL) {
+      const std::string h = (kind == OAT_KIND_DIM) ? "_decoder._locscale._model." : "_locscale._model.";
+      const HostTensor *w1 = P.get(h + "0.weight", {32, 64}), *b1 = P.get(h + "0.bias", {32}),
+                       *w2 = P.get(h + "2.weight", {4, 32}), *b2 = P.get(h + "2.bias", {4});
+      if (!w1 || !b1 || !w2 || !b2)
+        return fail(P.err + " (the flow head must be MLP(64,[32,4]); sequence.py:61 sizes it by T)");
+      for (int j = 0; j < 32; ++j) {
+        for (int k = 0; k < 64; ++k) fw[kFlowW1T + k * 32 + j] = w1->data[j * 64 + k];
+        fw[kFlowB1 + j] = b1->data[j];
+      }
+      for (int i = 0; i < 128; ++i) fw[kFlowW2 + i] = w2->data[i];
+      for (int i = 0; i < 4; ++i) fw[kFlowB2 + i] = b2->data[i];
+    } else {
+      const HostTensor *wo = P.get("_output.weight", {2, 64}), *bo = P.get("_output.bias", {2});
+      if (!wo || !bo) return fail(P.err);
+      for (int i = 0; i < 128; ++i) fw[kFlowW1T + i] = wo->data[i];
+      fw[kFlowB2 + 0] = bo->data[0];
+      fw[kFlowB2 + 1] = bo->data[1];
+    }
+  }
+
+  // ---- upload
+  OatModel* m = new OatModel();
+  m->kind = kind;
+  m->device = device;
+  m->in_channels = (int)C;
+  m->scalars = S;
+  m->arena_floats = P.arena.size();
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&m->arena, m->arena_floats * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->arena, P.arena.data(), m->arena_floats * sizeof(float), cudaMemcpyHostToDevice);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    if (m->arena) cudaFree(m->arena);
+    delete m;
+    return fail(std::string("oat_model_create: ") + cudaGetErrorString(e));
+  }
+  auto dev = [&](const Off& o) {
+    ConvW c;
+    c.w = m->arena + o.w;
+    c.b = m->arena + o.b;
+    return c;
+  };
+  m->stem = dev(stem);
+  for (const BlockOff& b : blocks) {
+    BlockW bw;
+    bw.cin = b.cin; bw.hid = b.hid; bw.cout = b.cout; bw.stride = b.stride;
+    bw.residual = b.residual; bw.hin = b.hin; bw.hout = b.hout;
+    if (b.hid != b.cin) bw.expand = dev(b.expand);
+    bw.dw = dev(b.dw);
+    bw.project = dev(b.project);
+    m->blocks.push_back(bw);
+  }
+  m->last = dev(last);
+  m->fc = dev(fc);
+  for (int i = 0; i < 3; ++i) m->merger[i] = dev(mg[i]);
+  m->flow = m->arena + flow.w;
+  *out = m;
+  return 0;
+}
+
+int oat_model_destroy(OatModel* model) {
+  if (!model) return 0;
+  if (model->arena) cudaFree(model->arena);
+  delete model;
+  return 0;
+}
+
+int oat_model_in_channels(const OatModel* model) { return model ? model->in_channels : -1; }
+
+int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble** out) {
+  if (!models || !out || num_models < 1) return fail("oat_ensemble_create: need >= 1 model");
+  if (num_models > kMaxModels) return fail("oat_ensemble_create: too many models for one GPU (max 16)");
+  OatEnsemble* e = new OatEnsemble();
+  for (int i = 0; i < num_models; ++i) {
+    if (!models[i]) { delete e; return fail("oat_ensemble_create: null model"); }
+    if (models[i]->kind == OAT_KIND_FLOW) { delete e; return fail("oat_ensemble_create: flow-only model has no encoder"); }
+    if (models[i]->device != models[0]->device || models[i]->kind != models[0]->kind ||
+        models[i]->in_channels != models[0]->in_channels) {
+      delete e;
+      return fail("oat_ensemble_create: models must share device, kind and in_channels");
+    }
+    e->models.push_back(models[i]);
+  }
+  e->device = models[0]->device;
+  *out = e;
+  return 0;
+}
+
+int oat_ensemble_destroy(OatEnsemble* ens) {
+  if (!ens) return 0;
+  if (ens->ws) cudaFree(ens->ws);
+  delete ens;
+  return 0;
+}
+
+int oat_ensemble_reserve(OatEnsemble* ens, int32_t batch) {
+  if (!ens) return fail("oat_ensemble_reserve: null ensemble");
+  if (batch <= ens->reserved_batch) return 0;
+  // per (model, image) floats: block in/out ping-pong, expanded, depthwise, pooled, feat
+  const size_t kA = 50 * 50 * 32, kH1 = 50 * 50 * 96, kH2 = 25 * 25 * 144;
+  const size_t per = 2 * kA + kH1 + kH2 + 1280 + 128;
+  const size_t EB = ens->models.size() * (size_t)batch;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  OAT_CUDA(cudaSetDevice(ens->device));
+  if (ens->ws) {
+    OAT_CUDA(cudaDeviceSynchronize());
+    OAT_CUDA(cudaFree(ens->ws));
+    ens->ws = nullptr;
+  }
+  cudaError_t e = cudaMalloc(&ens->ws, per * EB * sizeof(float));
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    ens->reserved_batch = 0;
+    return fail(std::string("oat_ensemble_reserve: ") + cudaGetErrorString(e));
+  }
+  float* p = ens->ws;
+  ens->bufA = p; p += kA * EB;
+  ens->bufB = p; p += kA * EB;
+  ens->bufH1 = p; p += kH1 * EB;
+  ens->bufH2 = p; p += kH2 * EB;
+  ens->pooled = p; p += 1280 * EB;
+  ens->feat = p;
+  ens->reserved_batch = batch;
+  return 0;
+}
+
+static int check_device(int want, const char* who) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) return fail(std::string(who) + ": no CUDA device");
+  if (cur != want)
+    return fail(std::string(who) + ": current CUDA device differs from the model's device");
+  return 0;
+}
+
+int oat_transform_visual(const float* lidar, int32_t B, int32_t C, int32_t H, int32_t W,
+                         float* visual, void* stream) {
+  if (!lidar || !visual) return fail("oat_transform_visual: null pointer");
+  if (H < 2 || W < 2) return fail("oat_transform_visual: input must be at least 2x2");
+  return launch_transform_visual(lidar, B, C, H, W, visual, (cudaStream_t)stream);
+}
+
+int oat_encode(OatEnsemble* ens, const float* visual, const float* scalars, int32_t B, float* z,
+               void* stream) {
+  if (!ens || !visual || !scalars || !z) return fail("oat_encode: null argument");
+  if (B <= 0) return 0;
+  if (int rc = check_device(ens->device, "oat_encode")) return rc;
+  if (int rc = oat_ensemble_reserve(ens, B)) return rc;
+  return encoder_forward(ens, visual, scalars, B, z, (cudaStream_t)stream);
+}
+
+static PtrTable one_model(const OatModel* m) {
+  PtrTable t;
+  for (int i = 0; i < kMaxModels; ++i) t.p[i] = nullptr;
+  t.p[0] = m->flow;
+  return t;
+}
+
+int oat_flow_forward(const OatModel* model, const float* x, const float* z, int64_t N, int32_t T,
+                     int32_t rows_per_z, float* y, float* logabsdet, void* stream) {
+  if (!model || !x || !z || !y) return fail("oat_flow_forward: null argument");
+  if (model->kind == OAT_KIND_CIL) return fail("oat_flow_forward: not a flow model");
+  if (int rc = check_device(model->device, "oat_flow_forward")) return rc;
+  FlowLaunch a{};
+  a.mode = 0; a.num_models = 1; a.weights = one_model(model);
+  a.in = x; a.z = z; a.z_model_stride = 0; a.out = y;
+  a.logprob = nullptr; a.logabsdet = logabsdet; a.q = nullptr; a.out_model_stride = 0;
+  a.goal = nullptr; a.G = 0; a.epsilon = 1.0f; a.N = N; a.T = T; a.rows_per_z = rows_per_z;
+  a.skip_model = -1;
+  return launch_flow(a, (cudaStream_t)stream);
+}
+
+int oat_flow_inverse(const OatModel* model, const float* y, const float* z, int64_t N, int32_t T,
+                     int32_t rows_per_z, float* x, float* log_prob, float* logabsdet,
+                     void* stream) {
+  if (!model || !y || !z) return fail("oat_flow_inverse: null argument");
+  if (model->kind == OAT_KIND_CIL) return fail("oat_flow_inverse: not a flow model");
+  if (int rc = check_device(model->device, "oat_flow_inverse")) return rc;
+  FlowLaunch a{};
+  a.mode = 1; a.num_models = 1; a.weights = one_model(model);
+  a.in = y; a.z = z; a.z_model_stride = 0; a.out = x;
+  a.logprob = log_prob; a.logabsdet = logabsdet; a.q = nullptr; a.out_model_stride = 0;
+  a.goal = nullptr; a.G = 0; a.epsilon = 1.0f; a.N = N; a.T = T; a.rows_per_z = rows_per_z;
+  a.skip_model = -1;
+  return launch_flow(a, (cudaStream_t)stream);
+}
+
+int oat_rip_sample_score(OatEnsemble* ens, int32_t proposal_idx, const float* z, const float* x,
+                         const float* goal, int32_t G, float epsilon, int32_t B, int32_t K,
+                         int32_t T, float* y, float* q, void* stream) {
+  if (!ens || !z || !y || !q) return fail("oat_rip_sample_score: null argument");
+  const int E = (int)ens->models.size();
+  if (proposal_idx >= E) return fail("oat_rip_sample_score: proposal_idx out of range");
+  if (proposal_idx >= 0 && !x) return fail("oat_rip_sample_score: x is required to sample");
+  if (goal && G < 1) return fail("oat_rip_sample_score: G must be >= 1 when goal is given");
+  if (epsilon <= 0.0f) return fail("oat_rip_sample_score: epsilon must be positive");
+  if (ens->models[0]->kind != OAT_KIND_DIM) return fail("oat_rip_sample_score: not ImitativeModels");
+  if (int rc = check_device(ens->device, "oat_rip_sample_score")) return rc;
+  const int64_t N = (int64_t)B * K;
+  if (N <= 0) return 0;
+  FlowLaunch a{};
+  a.goal = goal; a.G = G; a.epsilon = epsilon; a.N = N; a.T = T; a.rows_per_z = K;
+  a.logprob = nullptr; a.logabsdet = nullptr;
+  if (proposal_idx >= 0) {
+    // proposals y = f_p(x; z_p) (rip/agent.py:106); the same pass also emits q[p].
+    a.mode = 0; a.num_models = 1; a.weights = one_model(ens->models[proposal_idx]);
+    a.in = x; a.z = z + (int64_t)proposal_idx * B * kHidden; a.z_model_stride = 0;
+    a.out = y; a.q = q + (int64_t)proposal_idx * N; a.out_model_stride = 0; a.skip_model = -1;
+    if (int rc = launch_flow(a, (cudaStream_t)stream)) return rc;
+    if (E == 1) return 0;
+  }
+  // scores under every (other) local model (rip/agent.py:109-119)
+  a.mode = 1; a.num_models = E;
+  for (int i = 0; i < kMaxModels; ++i) a.weights.p[i] = i < E ? ens->models[i]->flow : nullptr;
+  a.in = y; a.z = z; a.z_model_stride = (int64_t)B * kHidden;
+  a.out = nullptr; a.q = q; a.out_model_stride = N; a.skip_model = proposal_idx;
+  return launch_flow(a, (cudaStream_t)stream);
+}
+
+int oat_rip_aggregate(const float* q, int32_t E, int32_t B, int32_t K, int32_t algo,
+                      const float* y, int32_t T, float* s, int32_t* kstar, float* sbest,
+                      float* plan, void* stream) {
+  if (!q || !kstar) return fail("oat_rip_aggregate: null argument");
+  if (plan && !y) return fail("oat_rip_aggregate: plan requested without y");
+  return launch_aggregate(q, E, B, K, algo, y, T, s, kstar, sbest, plan, (cudaStream_t)stream);
+}
+
+int oat_cil_rollout(const OatModel* model, const float* z, int32_t B, int32_t T, float* y,
+                    void* stream) {
+  if (!model || !z || !y) return fail("oat_cil_rollout: null argument");
+  if (model->kind != OAT_KIND_CIL) return fail("oat_cil_rollout: not a BehaviouralModel");
+  if (int rc = check_device(model->device, "oat_cil_rollout")) return rc;
+  FlowLaunch a{};
+  a.mode = 2; a.num_models = 1; a.weights = one_model(model);
+  a.in = nullptr; a.z = z; a.z_model_stride = 0; a.out = y;
+  a.N = B; a.T = T; a.rows_per_z = 1; a.skip_model = -1;
+  return launch_flow(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

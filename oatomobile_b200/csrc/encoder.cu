@@ -1,0 +1,446 @@
+// BEV encoder kernels (sm_100a), FP32 SIMT path.
+//
+// Replaces oatomobile/torch/transforms.py:34-49 (bilinear resize + transpose),
+// oatomobile/torch/networks/perception.py:53-55 (torchvision MobileNetV2 forward,
+// eval mode, BatchNorm folded at pack time) and the merger MLP of
+// oatomobile/baselines/torch/dim/model.py:203-217.
+//
+// Activations are NHWC fp32, grouped over the E models of the ensemble on
+// gridDim.z/.y so one launch serves every model ([E][B][H][W][C]); the 34
+// pointwise convolutions are [M=B*H*W, K] x [K, N] GEMMs with a fused
+// bias(+BN) / ReLU6 / residual epilogue.
+#include "common.cuh"
+
+namespace oat {
+namespace {
+
+__device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.0f), 6.0f); }
+
+// ---------------------------------------------------------------------------
+// a1. bilinear 2x-ish resize (align_corners=True) fused with the H<->W swap.
+// out[b,c,i,j] = R[b,c,j,i],  R[p,q] = bilinear(src, p*(H-1)/(OH-1), q*(W-1)/(OW-1)).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transform_visual_kernel(
+    const float* __restrict__ lidar, int BC, int H, int W, float* __restrict__ out,
+    float scale_h, float scale_w) {
+  constexpr int O = 100;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)BC * O * O) return;
+  const int j = (int)(idx % O);          // output column  = resized row index p
+  const int i = (int)((idx / O) % O);    // output row     = resized column index q
+  const int64_t bc = idx / (O * O);
+  const int p = j, qq = i;
+  const float sy = scale_h * (float)p, sx = scale_w * (float)qq;
+  const int y0 = min((int)sy, H - 1), x0 = min((int)sx, W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float hy = 1.0f - ly, hx = 1.0f - lx;
+  const float* src = lidar + bc * H * W;
+  const float v00 = __ldg(src + y0 * W + x0), v01 = __ldg(src + y0 * W + x1);
+  const float v10 = __ldg(src + y1 * W + x0), v11 = __ldg(src + y1 * W + x1);
+  // same association as ATen: hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11)
+  out[idx] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+}
+
+// ---------------------------------------------------------------------------
+// stem: 3x3 stride-2 pad-1 conv C->32 + folded BN + ReLU6 (features.0).
+// in NCHW [B,C,100,100] (shared by all models) -> out [E][B][50][50][32].
+// ---------------------------------------------------------------------------
+constexpr int STEM_THREADS = 128;
+constexpr int STEM_MAXC = 8;
+
+__global__ void __launch_bounds__(STEM_THREADS) stem_kernel(
+    const __grid_constant__ PtrTable w, const __grid_constant__ PtrTable bias, const float* __restrict__ vis, int B, int C,
+    float* __restrict__ out) {
+  __shared__ __align__(16) float ws[9 * STEM_MAXC * 32];
+  __shared__ __align__(16) float bs[32];
+  const int model = blockIdx.y;
+  for (int i = threadIdx.x; i < 9 * C * 32; i += STEM_THREADS) ws[i] = __ldg(w.p[model] + i);
+  if (threadIdx.x < 32) bs[threadIdx.x] = __ldg(bias.p[model] + threadIdx.x);
+  __syncthreads();
+  const int64_t pix = (int64_t)blockIdx.x * STEM_THREADS + threadIdx.x;
+  if (pix >= (int64_t)B * 2500) return;
+  const int ow = (int)(pix % 50), oh = (int)((pix / 50) % 50);
+  const int64_t b = pix / 2500;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = bs[i];
+  for (int c = 0; c < C; ++c) {
+    const float* plane = vis + (b * C + c) * 10000;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = 2 * oh - 1 + kh;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = 2 * ow - 1 + kw;
+        float v = 0.0f;
+        if (ih >= 0 && ih < 100 && iw >= 0 && iw < 100) v = __ldg(plane + ih * 100 + iw);
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((kh * 3 + kw) * C + c) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 wv = wr[j];
+          acc[4 * j + 0] = fmaf(v, wv.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(v, wv.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, wv.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(v, wv.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(out + ((int64_t)model * B * 2500 + pix) * 32);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    dst[j] = make_float4(relu6f(acc[4 * j]), relu6f(acc[4 * j + 1]), relu6f(acc[4 * j + 2]),
+                         relu6f(acc[4 * j + 3]));
+}
+
+// ---------------------------------------------------------------------------
+// pointwise (1x1) convolution = GEMM  C[M,N] = act(A[M,K] W[K,N] + bias) (+ R).
+// 256 threads, BK = 8, register-prefetched double-buffered smem tiles.
+// ---------------------------------------------------------------------------
+struct PwArgs {
+  PtrTable w, bias;
+  const float* A;
+  float* C;
+  const float* R;        // residual or null
+  int64_t a_stride;      // floats between models in A (0 = shared input)
+  int64_t c_stride;      // floats between models in C / R
+  int M, K, N;
+  int relu6;
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) pw_gemm_kernel(const __grid_constant__ PwArgs a) {
+  constexpr int BK = 8;
+  constexpr int NTX = BN / TN;            // threads along n
+  constexpr int AS_LD = BM + 4;           // padded leading dim of the transposed A tile
+  constexpr int A_F4 = BM * BK / 4 / 256; // float4 loads of A per thread
+  static_assert((BM / TM) * NTX == 256, "tile/thread mismatch");
+  static_assert(A_F4 >= 1, "A tile too small");
+  __shared__ __align__(16) float As[2][BK][AS_LD];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const int tid = threadIdx.x;
+  const int model = blockIdx.z;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const float* __restrict__ A = a.A + (int64_t)model * a.a_stride;
+  const float* __restrict__ W = a.w.p[model];
+  const int M = a.M, K = a.K, N = a.N;
+
+  const int tx = tid % NTX, ty = tid / NTX;
+
+  float4 areg[A_F4];
+  float4 breg = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int b_k = tid / (BN / 4), b_n4 = tid % (BN / 4);
+  const bool b_active = tid < BK * BN / 4;
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_F4; ++i) {
+      const int f = tid + i * 256;
+      const int row = f / 2, kq = f % 2;
+      const int gm = m0 + row;
+      areg[i] = (gm < M) ? __ldg(reinterpret_cast<const float4*>(A + (int64_t)gm * K + k0 + 4 * kq))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (b_active) {
+      const int gn = n0 + 4 * b_n4;
+      breg = (gn < N) ? __ldg(reinterpret_cast<const float4*>(W + (int64_t)(k0 + b_k) * N + gn))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_F4; ++i) {
+      const int f = tid + i * 256;
+      const int row = f / 2, kq = f % 2;
+      As[buf][4 * kq + 0][row] = areg[i].x;
+      As[buf][4 * kq + 1][row] = areg[i].y;
+      As[buf][4 * kq + 2][row] = areg[i].z;
+      As[buf][4 * kq + 3][row] = areg[i].w;
+    }
+    if (b_active) *reinterpret_cast<float4*>(&Bs[buf][b_k][4 * b_n4]) = breg;
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+  const int nk = K / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float af[TM], bf[TN];
+#pragma unroll
+      for (int i = 0; i < TM / 4; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + 4 * i]);
+        af[4 * i] = v.x; af[4 * i + 1] = v.y; af[4 * i + 2] = v.z; af[4 * i + 3] = v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TN / 4; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN + 4 * j]);
+        bf[4 * j] = v.x; bf[4 * j + 1] = v.y; bf[4 * j + 2] = v.z; bf[4 * j + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue: folded-BN bias, ReLU6, residual ------------------------------
+  const float* __restrict__ bias = a.bias.p[model];
+  float* __restrict__ C = a.C + (int64_t)model * a.c_stride;
+  const float* __restrict__ R = a.R ? a.R + (int64_t)model * a.c_stride : nullptr;
+#pragma unroll
+  for (int j = 0; j < TN / 4; ++j) {
+    const int gn = n0 + tx * TN + 4 * j;
+    if (gn >= N) continue;
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + gn));
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int gm = m0 + ty * TM + i;
+      if (gm >= M) continue;
+      float4 v = make_float4(acc[i][4 * j] + bv.x, acc[i][4 * j + 1] + bv.y,
+                             acc[i][4 * j + 2] + bv.z, acc[i][4 * j + 3] + bv.w);
+      if (a.relu6) { v.x = relu6f(v.x); v.y = relu6f(v.y); v.z = relu6f(v.z); v.w = relu6f(v.w); }
+      if (R) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(R + (int64_t)gm * N + gn));
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      *reinterpret_cast<float4*>(C + (int64_t)gm * N + gn) = v;
+    }
+  }
+}
+
+int launch_pw(const PwArgs& a, int E, cudaStream_t stream) {
+  if (a.K % 8 != 0 || a.N % 4 != 0) return fail("pw_gemm: K must be a multiple of 8, N of 4");
+  if (a.N <= 16) {
+    dim3 grid((a.M + 255) / 256, (a.N + 15) / 16, E);
+    pw_gemm_kernel<256, 16, 4, 4><<<grid, 256, 0, stream>>>(a);
+  } else if (a.N <= 32 || a.N == 96) {
+    dim3 grid((a.M + 127) / 128, (a.N + 31) / 32, E);
+    pw_gemm_kernel<128, 32, 4, 4><<<grid, 256, 0, stream>>>(a);
+  } else {
+    dim3 grid((a.M + 127) / 128, (a.N + 63) / 64, E);
+    pw_gemm_kernel<128, 64, 8, 4><<<grid, 256, 0, stream>>>(a);
+  }
+  OAT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// depthwise 3x3 (pad 1, stride 1|2) + folded BN + ReLU6, NHWC, float4 channels.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dw_kernel(const __grid_constant__ PtrTable w,
+                                                 const __grid_constant__ PtrTable bias,
+                                                 const float* __restrict__ in,
+                                                 float* __restrict__ out, int B, int Hin,
+                                                 int Hout, int C, int stride) {
+  const int model = blockIdx.y;
+  const int C4 = C >> 2;
+  const int64_t total = (int64_t)B * Hout * Hout * C4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  const int64_t p = idx / C4;
+  const int ow = (int)(p % Hout), oh = (int)((p / Hout) % Hout);
+  const int64_t b = p / ((int64_t)Hout * Hout);
+  const float* __restrict__ wm = w.p[model];
+  const float* __restrict__ src = in + ((int64_t)model * B + b) * Hin * Hin * C;
+  float4 acc = __ldg(reinterpret_cast<const float4*>(bias.p[model] + 4 * c4));
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = oh * stride - 1 + kh;
+    if (ih < 0 || ih >= Hin) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int iw = ow * stride - 1 + kw;
+      if (iw < 0 || iw >= Hin) continue;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)ih * Hin + iw) * C + 4 * c4));
+      const float4 k = __ldg(reinterpret_cast<const float4*>(wm + (kh * 3 + kw) * C + 4 * c4));
+      acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y);
+      acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+    }
+  }
+  acc.x = relu6f(acc.x); acc.y = relu6f(acc.y); acc.z = relu6f(acc.z); acc.w = relu6f(acc.w);
+  *reinterpret_cast<float4*>(out + (((int64_t)model * B + b) * Hout * Hout + (int64_t)oh * Hout + ow) * C + 4 * c4) = acc;
+}
+
+// ---------------------------------------------------------------------------
+// global average pool over P pixels: [E*B][P][C] -> [E*B][C].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ in,
+                                                   float* __restrict__ out, int64_t rows,
+                                                   int P, int C) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * C) return;
+  const int c = (int)(idx % C);
+  const int64_t r = idx / C;
+  const float* src = in + r * P * C + c;
+  float s = 0.0f;
+  for (int p = 0; p < P; ++p) s += __ldg(src + (int64_t)p * C);
+  out[idx] = s / (float)P;
+}
+
+// ---------------------------------------------------------------------------
+// merger MLP: z = relu(W2 relu(W1 relu(W0 [feat, scalars] + b0) + b1) + b2)
+// (dim/model.py:205-217, mlp.py:49-66).  One CTA of 64 threads per (model,row).
+// ---------------------------------------------------------------------------
+struct MergerArgs {
+  PtrTable w0, b0, w1, b1, w2, b2;  // transposed weights [in][64]
+  const float* feat;     // [E][B][128]
+  const float* scalars;  // [B][S]
+  int B, S;
+  float* z;              // [E][B][64]
+};
+
+__global__ void __launch_bounds__(64) merger_kernel(const __grid_constant__ MergerArgs a) {
+  __shared__ float u[OAT_ENC_FEATURES + 8];
+  __shared__ float v[64];
+  const int model = blockIdx.y, b = blockIdx.x, j = threadIdx.x;
+  const int in0 = OAT_ENC_FEATURES + a.S;
+  const float* f = a.feat + ((int64_t)model * a.B + b) * OAT_ENC_FEATURES;
+  u[j] = __ldg(f + j);
+  u[j + 64] = __ldg(f + j + 64);
+  if (j < a.S) u[OAT_ENC_FEATURES + j] = __ldg(a.scalars + (int64_t)b * a.S + j);
+  __syncthreads();
+  float acc = __ldg(a.b0.p[model] + j);
+  const float* w = a.w0.p[model];
+  for (int i = 0; i < in0; ++i) acc = fmaf(u[i], __ldg(w + i * 64 + j), acc);
+  v[j] = fmaxf(acc, 0.0f);
+  __syncthreads();
+  acc = __ldg(a.b1.p[model] + j);
+  w = a.w1.p[model];
+  for (int i = 0; i < 64; ++i) acc = fmaf(v[i], __ldg(w + i * 64 + j), acc);
+  __syncthreads();
+  u[j] = fmaxf(acc, 0.0f);
+  __syncthreads();
+  acc = __ldg(a.b2.p[model] + j);
+  w = a.w2.p[model];
+  for (int i = 0; i < 64; ++i) acc = fmaf(u[i], __ldg(w + i * 64 + j), acc);
+  a.z[((int64_t)model * a.B + b) * 64 + j] = fmaxf(acc, 0.0f);
+}
+
+}  // namespace
+
+int launch_transform_visual(const float* lidar, int B, int C, int H, int W, float* visual,
+                            cudaStream_t stream) {
+  if (B <= 0) return 0;
+  const int64_t total = (int64_t)B * C * 100 * 100;
+  // ATen: scale = (in-1)/(out-1) evaluated in float for align_corners=True
+  const float sh = (float)(H - 1) / 99.0f, sw = (float)(W - 1) / 99.0f;
+  transform_visual_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      lidar, B * C, H, W, visual, sh, sw);
+  OAT_LAUNCH_CHECK();
+  return 0;
+}
+
+int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars, int B,
+                    float* z, cudaStream_t stream) {
+  const int E = (int)ens->models.size();
+  const OatModel* m0 = ens->models[0];
+  const int C = m0->in_channels;
+  if (C > STEM_MAXC) return fail("encoder: in_channels > 8 unsupported");
+  auto table = [&](auto getter) {
+    PtrTable t;
+    for (int e = 0; e < kMaxModels; ++e) t.p[e] = nullptr;
+    for (int e = 0; e < E; ++e) t.p[e] = getter(ens->models[e]);
+    return t;
+  };
+
+  // stem -> bufA [E][B][50][50][32]
+  {
+    PtrTable w = table([](const OatModel* m) { return m->stem.w; });
+    PtrTable b = table([](const OatModel* m) { return m->stem.b; });
+    dim3 grid((unsigned)(((int64_t)B * 2500 + STEM_THREADS - 1) / STEM_THREADS), E);
+    stem_kernel<<<grid, STEM_THREADS, 0, stream>>>(w, b, visual, B, C, ens->bufA);
+    OAT_LAUNCH_CHECK();
+  }
+  float* x = ens->bufA;
+  float* y = ens->bufB;
+  for (size_t bi = 0; bi < m0->blocks.size(); ++bi) {
+    const BlockW& blk = m0->blocks[bi];
+    const int Min = B * blk.hin * blk.hin, Mout = B * blk.hout * blk.hout;
+    const float* dw_in = x;
+    if (blk.hid != blk.cin) {  // expand 1x1 + BN + ReLU6
+      PwArgs a;
+      a.w = table([bi](const OatModel* m) { return m->blocks[bi].expand.w; });
+      a.bias = table([bi](const OatModel* m) { return m->blocks[bi].expand.b; });
+      a.A = x; a.C = ens->bufH1; a.R = nullptr;
+      a.a_stride = (int64_t)Min * blk.cin; a.c_stride = (int64_t)Min * blk.hid;
+      a.M = Min; a.K = blk.cin; a.N = blk.hid; a.relu6 = 1;
+      if (int rc = launch_pw(a, E, stream)) return rc;
+      dw_in = ens->bufH1;
+    }
+    {  // depthwise 3x3 + BN + ReLU6
+      PtrTable w = table([bi](const OatModel* m) { return m->blocks[bi].dw.w; });
+      PtrTable b = table([bi](const OatModel* m) { return m->blocks[bi].dw.b; });
+      const int64_t total = (int64_t)Mout * (blk.hid / 4);
+      dim3 grid((unsigned)((total + 255) / 256), E);
+      dw_kernel<<<grid, 256, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid,
+                                         blk.stride);
+      OAT_LAUNCH_CHECK();
+    }
+    {  // project 1x1 + BN (linear) + residual
+      PwArgs a;
+      a.w = table([bi](const OatModel* m) { return m->blocks[bi].project.w; });
+      a.bias = table([bi](const OatModel* m) { return m->blocks[bi].project.b; });
+      a.A = ens->bufH2; a.C = y; a.R = blk.residual ? x : nullptr;
+      a.a_stride = (int64_t)Mout * blk.hid; a.c_stride = (int64_t)Mout * blk.cout;
+      a.M = Mout; a.K = blk.hid; a.N = blk.cout; a.relu6 = 0;
+      if (int rc = launch_pw(a, E, stream)) return rc;
+    }
+    float* t = x; x = y; y = t;
+  }
+  const int hl = m0->blocks.back().hout;  // 4
+  const int P = hl * hl;
+  {  // features.18: 1x1 320->1280 + BN + ReLU6 -> bufH1 [E][B*P][1280]
+    PwArgs a;
+    a.w = table([](const OatModel* m) { return m->last.w; });
+    a.bias = table([](const OatModel* m) { return m->last.b; });
+    a.A = x; a.C = ens->bufH1; a.R = nullptr;
+    a.a_stride = (int64_t)B * P * 320; a.c_stride = (int64_t)B * P * 1280;
+    a.M = B * P; a.K = 320; a.N = 1280; a.relu6 = 1;
+    if (int rc = launch_pw(a, E, stream)) return rc;
+  }
+  {  // global average pool -> pooled [E][B][1280]
+    const int64_t rows = (int64_t)E * B;
+    pool_kernel<<<(unsigned)((rows * 1280 + 255) / 256), 256, 0, stream>>>(ens->bufH1, ens->pooled,
+                                                                          rows, P, 1280);
+    OAT_LAUNCH_CHECK();
+  }
+  {  // classifier.1: Linear 1280 -> 128 (Dropout is identity in eval)
+    PwArgs a;
+    a.w = table([](const OatModel* m) { return m->fc.w; });
+    a.bias = table([](const OatModel* m) { return m->fc.b; });
+    a.A = ens->pooled; a.C = ens->feat; a.R = nullptr;
+    a.a_stride = (int64_t)B * 1280; a.c_stride = (int64_t)B * 128;
+    a.M = B; a.K = 1280; a.N = 128; a.relu6 = 0;
+    if (int rc = launch_pw(a, E, stream)) return rc;
+  }
+  {  // merger MLP -> z [E][B][64]
+    MergerArgs a;
+    a.w0 = table([](const OatModel* m) { return m->merger[0].w; });
+    a.b0 = table([](const OatModel* m) { return m->merger[0].b; });
+    a.w1 = table([](const OatModel* m) { return m->merger[1].w; });
+    a.b1 = table([](const OatModel* m) { return m->merger[1].b; });
+    a.w2 = table([](const OatModel* m) { return m->merger[2].w; });
+    a.b2 = table([](const OatModel* m) { return m->merger[2].b; });
+    a.feat = ens->feat; a.scalars = scalars; a.B = B; a.S = m0->scalars; a.z = z;
+    merger_kernel<<<dim3(B, E), 64, 0, stream>>>(a);
+    OAT_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace oat

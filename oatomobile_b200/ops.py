@@ -1,0 +1,134 @@
+"""Thin functional wrappers: torch CUDA tensors in/out, kernels from liboat_b200.so.
+
+PyTorch is only the allocator/stream provider here; every number is produced by
+the hand-written sm_100a kernels behind the C-ABI (include/oat_b200.h).
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from oatomobile_b200 import _native as N
+
+
+def transform_visual(lidar: torch.Tensor) -> torch.Tensor:
+  """oatomobile/torch/transforms.py:34-49 — [B,C,H,W] -> [B,C,100,100] (resize + H<->W)."""
+  lidar = N.require_cuda_f32(lidar, "lidar")
+  B, C, H, W = lidar.shape
+  out = torch.empty(B, C, 100, 100, device=lidar.device, dtype=torch.float32)
+  with torch.cuda.device(lidar.device):
+    N.check(N.lib().oat_transform_visual(lidar.data_ptr(), B, C, H, W, out.data_ptr(),
+                                         N.stream_ptr(lidar.device)))
+  return out
+
+
+def encode(ens: N.EnsembleHandle, visual: torch.Tensor, scalars: torch.Tensor) -> torch.Tensor:
+  """dim/model.py:173-219 for all E models: -> z [E,B,64]."""
+  visual = N.require_cuda_f32(visual, "visual_features")
+  scalars = N.require_cuda_f32(scalars, "scalars")
+  B = visual.shape[0]
+  if tuple(visual.shape[2:]) != (100, 100):
+    raise ValueError("`visual_features` must be [B,C,100,100] (apply `model.transform` first), "
+                     "got %s" % (tuple(visual.shape),))
+  z = torch.empty(len(ens), B, 64, device=visual.device, dtype=torch.float32)
+  with torch.cuda.device(visual.device):
+    N.check(N.lib().oat_encode(ens.ptr, visual.data_ptr(), scalars.data_ptr(), B, z.data_ptr(),
+                               N.stream_ptr(visual.device)))
+  return z
+
+
+def flow_forward(model: N.ModelHandle, x: torch.Tensor, z: torch.Tensor,
+                 rows_per_z: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+  """sequence.py:95-151 — x [N,T,2], z [N/rows_per_z,64] -> y, logabsdet."""
+  x = N.require_cuda_f32(x, "x")
+  z = N.require_cuda_f32(z, "z")
+  n, T, _ = x.shape
+  if z.shape[0] * rows_per_z != n:
+    raise ValueError("z has %d rows, expected %d" % (z.shape[0], n // max(rows_per_z, 1)))
+  y = torch.empty_like(x)
+  lad = torch.empty(n, device=x.device, dtype=torch.float32)
+  with torch.cuda.device(x.device):
+    N.check(N.lib().oat_flow_forward(model.ptr, x.data_ptr(), z.data_ptr(), n, T, rows_per_z,
+                                     y.data_ptr(), lad.data_ptr(), N.stream_ptr(x.device)))
+  return y, lad
+
+
+def flow_inverse(model: N.ModelHandle, y: torch.Tensor, z: torch.Tensor, rows_per_z: int = 1,
+                 want_x: bool = True):
+  """sequence.py:153-216 — y [N,T,2] -> x, log_prob, logabsdet."""
+  y = N.require_cuda_f32(y, "y")
+  z = N.require_cuda_f32(z, "z")
+  n, T, _ = y.shape
+  if z.shape[0] * rows_per_z != n:
+    raise ValueError("z has %d rows, expected %d" % (z.shape[0], n // max(rows_per_z, 1)))
+  x = torch.empty_like(y) if want_x else None
+  lp = torch.empty(n, device=y.device, dtype=torch.float32)
+  lad = torch.empty(n, device=y.device, dtype=torch.float32)
+  with torch.cuda.device(y.device):
+    N.check(N.lib().oat_flow_inverse(model.ptr, y.data_ptr(), z.data_ptr(), n, T, rows_per_z,
+                                     N.ptr(x), lp.data_ptr(), lad.data_ptr(),
+                                     N.stream_ptr(y.device)))
+  return x, lp, lad
+
+
+def rip_sample_score(ens: N.EnsembleHandle, z: torch.Tensor, x: Optional[torch.Tensor],
+                     goal: Optional[torch.Tensor], epsilon: float, proposal_idx: int = 0,
+                     y: Optional[torch.Tensor] = None, q: Optional[torch.Tensor] = None):
+  """z [E,B,64], x [B,K,T,2] -> y [B,K,T,2], q [E,B,K].
+
+  With `proposal_idx = -1` the proposals `y` are an input (sharded ensembles)."""
+  z = N.require_cuda_f32(z, "z")
+  E, B, _ = z.shape
+  if E != len(ens):
+    raise ValueError("z has %d models, the ensemble %d" % (E, len(ens)))
+  if proposal_idx >= 0:
+    x = N.require_cuda_f32(x, "x")
+    _, K, T, _ = x.shape
+    if y is None:
+      y = torch.empty_like(x)
+  else:
+    y = N.require_cuda_f32(y, "y")
+    _, K, T, _ = y.shape
+  if goal is not None:
+    goal = N.require_cuda_f32(goal, "goal")
+  G = 0 if goal is None else goal.shape[1]
+  if q is None:
+    q = torch.empty(E, B, K, device=z.device, dtype=torch.float32)
+  with torch.cuda.device(z.device):
+    N.check(N.lib().oat_rip_sample_score(ens.ptr, proposal_idx, z.data_ptr(), N.ptr(x),
+                                         N.ptr(goal), G, float(epsilon), B, K, T, y.data_ptr(),
+                                         q.data_ptr(), N.stream_ptr(z.device)))
+  return y, q
+
+
+def rip_aggregate(q: torch.Tensor, y: Optional[torch.Tensor], algorithm: str,
+                  want_s: bool = False):
+  """rip/agent.py:121-127,137 — q [E,B,K] -> (kstar int32 [B], sbest [B], plan [B,T,2], s)."""
+  if algorithm not in N.ALGORITHMS:
+    raise AssertionError("algorithm must be one of WCM, MA, BCM")
+  q = N.require_cuda_f32(q, "q")
+  E, B, K = q.shape
+  T = 0
+  plan = None
+  if y is not None:
+    y = N.require_cuda_f32(y, "y")
+    T = y.shape[2]
+    plan = torch.empty(B, T, 2, device=q.device, dtype=torch.float32)
+  s = torch.empty(B, K, device=q.device, dtype=torch.float32) if want_s else None
+  kstar = torch.empty(B, device=q.device, dtype=torch.int32)
+  sbest = torch.empty(B, device=q.device, dtype=torch.float32)
+  with torch.cuda.device(q.device):
+    N.check(N.lib().oat_rip_aggregate(q.data_ptr(), E, B, K, N.ALGORITHMS[algorithm], N.ptr(y), T,
+                                      N.ptr(s), kstar.data_ptr(), sbest.data_ptr(), N.ptr(plan),
+                                      N.stream_ptr(q.device)))
+  return kstar, sbest, plan, s
+
+
+def cil_rollout(model: N.ModelHandle, z: torch.Tensor, T: int) -> torch.Tensor:
+  """cil/model.py:106-127 — z [B,64] -> y [B,T,2]."""
+  z = N.require_cuda_f32(z, "z")
+  B = z.shape[0]
+  y = torch.empty(B, T, 2, device=z.device, dtype=torch.float32)
+  with torch.cuda.device(z.device):
+    N.check(N.lib().oat_cil_rollout(model.ptr, z.data_ptr(), B, T, y.data_ptr(),
+                                    N.stream_ptr(z.device)))
+  return y

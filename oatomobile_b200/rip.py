@@ -1,0 +1,113 @@
+"""K-sample RIP sample-and-score (the BASELINE.json metric), single- and multi-GPU.
+
+Assembled from the reference's own primitives:
+  z_m   = models[m]._params(**ctx)                      dim/model.py:173-219
+  y     = models[0]._decoder._forward(x, z_0)           rip/agent.py:106,137
+  q_m   = log_prob_m(y) - logabsdet_m(y) (+ goal ll)    rip/agent.py:109-119
+  s     = min|max|mean_m(-q_m)   ("WCM"|"BCM"|"MA")     rip/agent.py:121-127
+  k*    = argmin_k s ; plan = y[b, k*]
+
+Multi-GPU: the ensemble is sharded in contiguous blocks of
+E/R models per rank.  One tiny broadcast of z_0 lets every rank regenerate the
+*identical* proposals y with the (replicated, 61 KB) decoder of model 0; the only
+data-path collective is then a single all-gather of the per-model scores q
+(`[E_local,B,K]` fp32 per rank) over NCCL/NVLink.  Every rank aggregates the same
+gathered tensor, so `k*` and the plan are bit-identical on all ranks.
+"""
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from oatomobile_b200 import _native as N
+from oatomobile_b200 import ops
+from oatomobile_b200.models import ImitativeModel, _CONTEXT_KEYS, _require, _scalars
+
+
+class RIPScorer:
+  """Scores K sampled trajectories per scene under an ensemble of ImitativeModels."""
+
+  def __init__(self, models: Sequence[ImitativeModel], algorithm: str = "WCM",
+               group=None, proposal_model: Optional[ImitativeModel] = None) -> None:
+    """Args:
+      models: the models owned by THIS rank (all E of them on one GPU).
+      algorithm: "WCM" | "MA" | "BCM", semantics as written at rip/agent.py:121-127.
+      group: optional torch.distributed process group the ensemble is sharded over
+        (rank r owns global models [r*E_local, (r+1)*E_local)).
+      proposal_model: on ranks that do not own global model 0, a replica of it (only
+        its flow decoder is used) so proposals can be regenerated locally.
+    """
+    assert algorithm in ("WCM", "MA", "BCM")  # rip/agent.py:43
+    self._algorithm = algorithm
+    self._models = list(models)
+    self._group = group
+    self._rank, self._world = 0, 1
+    if group is not None:
+      import torch.distributed as dist
+      self._rank, self._world = dist.get_rank(group), dist.get_world_size(group)
+    self._proposal_model = proposal_model
+    if self._world > 1 and self._rank != 0 and proposal_model is None:
+      raise ValueError("ranks other than 0 need `proposal_model` (a replica of global model 0)")
+    self._ens = None
+    self._ens_key = None
+
+  # ---- handles ---------------------------------------------------------------
+  def _ensemble(self) -> N.EnsembleHandle:
+    handles = [m.native_handle() for m in self._models]
+    key = tuple(id(h) for h in handles)
+    if key != self._ens_key:
+      self._ens = N.EnsembleHandle(handles)
+      self._ens_key = key
+    return self._ens
+
+  @property
+  def num_local_models(self) -> int:
+    return len(self._models)
+
+  # ---- stages ----------------------------------------------------------------
+  def encode(self, **context: torch.Tensor) -> torch.Tensor:
+    """E_local x `_params` in grouped launches → z [E_local,B,64]."""
+    _require(context, _CONTEXT_KEYS)
+    return ops.encode(self._ensemble(), context["visual_features"],
+                      _scalars(context, _CONTEXT_KEYS[1:]))
+
+  def score(self, z: torch.Tensor, x: torch.Tensor, goal: Optional[torch.Tensor] = None,
+            epsilon: float = 1.0, want_s: bool = False) -> Dict[str, torch.Tensor]:
+    """z [E_local,B,64], x [B,K,T,2] → plan/kstar/sbest (+ y, q, s)."""
+    ens = self._ensemble()
+    if self._world == 1:
+      y, q = ops.rip_sample_score(ens, z, x, goal, epsilon, proposal_idx=0)
+    else:
+      import torch.distributed as dist
+      # (1) z_0 from the owner of model 0 (64 floats per scene).
+      z0 = z[0].contiguous() if self._rank == 0 else torch.empty_like(z[0])
+      dist.broadcast(z0, src=dist.get_global_rank(self._group, 0), group=self._group)
+      if self._rank == 0:
+        y, q = ops.rip_sample_score(ens, z, x, goal, epsilon, proposal_idx=0)
+      else:
+        # (2) identical proposals, regenerated locally from the replicated decoder.
+        y, _ = ops.flow_forward(self._proposal_model._decoder._handle(),
+                                x.reshape(-1, x.shape[2], 2), z0, rows_per_z=x.shape[1])
+        y = y.view_as(x)
+        _, q = ops.rip_sample_score(ens, z, None, goal, epsilon, proposal_idx=-1, y=y)
+      # (3) the single data-path collective: all-gather of per-model scores.
+      q_all = torch.empty(self._world * q.shape[0], q.shape[1], q.shape[2], device=q.device,
+                          dtype=q.dtype)
+      dist.all_gather_into_tensor(q_all, q.contiguous(), group=self._group)
+      q = q_all
+    kstar, sbest, plan, s = ops.rip_aggregate(q, y, self._algorithm, want_s=want_s)
+    out = dict(plan=plan, kstar=kstar, sbest=sbest, y=y, q=q)
+    if want_s:
+      out["s"] = s
+    return out
+
+  def __call__(self, x: torch.Tensor, goal: Optional[torch.Tensor] = None, epsilon: float = 1.0,
+               want_s: bool = False, **context: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Full step of the metric on device-resident inputs.  `context` holds either
+    `lidar` [B,C,200,200] (raw) or `visual_features` [B,C,100,100] (transformed)."""
+    if "lidar" in context:
+      context = dict(context)
+      context["visual_features"] = ops.transform_visual(context.pop("lidar"))
+    z = self.encode(**context)
+    out = self.score(z, x, goal, epsilon, want_s)
+    out["z"] = z
+    return out

@@ -1,0 +1,155 @@
+"""TEST INFRASTRUCTURE ONLY — import shim for the *real* reference (OATML/oatomobile).
+
+Only usable where ``/root/reference`` exists (the build container, NOT the GPU
+box).  It is used by ``tests/golden/make_golden.py`` to generate the committed
+golden vectors and by ``tests/test_oracle_vs_reference.py`` to pin the in-repo
+restatement (``oracle/restatement.py``) against the reference itself.
+
+Nothing on the product path may import this module.
+
+What the shim does:
+  1. stubs ``gym`` / ``imageio`` / ``matplotlib`` (absent here, imported eagerly
+     by ``oatomobile/__init__.py`` and ``oatomobile/core/rl.py:23-24``);
+  2. puts ``/root/reference`` on ``sys.path``;
+  3. replaces ``torch.hub.load`` (network) with the local torchvision
+     ``mobilenet_v2`` constructor — the hub pin is
+     ``oatomobile/torch/networks/perception.py:36-40``;
+  4. ``fix_locscale(model)``: for T != 4 swaps ``_decoder._locscale`` for
+     ``MLP(64, [32, 4])`` (``oatomobile/torch/networks/sequence.py:61`` sizes the
+     head by T; the single sanctioned deviation);
+  5. ``set_in_channels(model, C)``: rebuilds the stem conv exactly like
+     ``perception.py:43-51`` does, for C != 2 (BASELINE.json uses C=4).
+"""
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("OAT_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+  return os.path.isdir(os.path.join(REFERENCE_ROOT, "oatomobile"))
+
+
+def _stub(name, **attrs):
+  if name in sys.modules:
+    return sys.modules[name]
+  m = types.ModuleType(name)
+  for k, v in attrs.items():
+    setattr(m, k, v)
+  sys.modules[name] = m
+  return m
+
+
+_installed = False
+
+
+def install():
+  """Makes ``import oatomobile`` work on CPU without CARLA/gym/network."""
+  global _installed
+  if _installed:
+    return
+  if not available():
+    raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+  import torch
+  import torchvision
+
+  class _Env:  # gym.Env / gym.Wrapper stand-ins
+    metadata = {}
+
+    def __init__(self, *a, **k):
+      pass
+
+  class _Space:
+
+    def __init__(self, *a, **k):
+      pass
+
+  spaces = _stub("gym.spaces", Box=_Space, Dict=_Space, Discrete=_Space,
+                 Space=_Space, Tuple=_Space, MultiDiscrete=_Space)
+  _stub("gym", Env=_Env, Wrapper=_Env, spaces=spaces, Space=_Space,
+        ObservationWrapper=_Env, ActionWrapper=_Env, RewardWrapper=_Env)
+  _stub("imageio")
+  plt = _stub("matplotlib.pyplot")
+  _stub("matplotlib", use=lambda *a, **k: None, pyplot=plt)
+  for extra in ("tree", "wget", "pygame", "transforms3d", "skimage", "seaborn"):
+    try:
+      __import__(extra)
+    except Exception:  # absent: harmless stub, never touched on the hot path
+      _stub(extra)
+
+  if REFERENCE_ROOT not in sys.path:
+    sys.path.insert(0, REFERENCE_ROOT)
+
+  def _hub_load(github=None, model=None, *a, **k):
+    assert model == "mobilenet_v2", model
+    return torchvision.models.mobilenet_v2(*a, **k)
+
+  torch.hub.load = _hub_load
+  _installed = True
+
+
+def fix_locscale(model):
+  """sequence.py:59-65 sizes the head by T; restore width 4 for T != 4."""
+  from oatomobile.torch.networks.mlp import MLP
+  import torch.nn as nn
+  if model._output_shape[0] != 4:
+    model._decoder._locscale = MLP(input_size=64, output_sizes=[32, 4],
+                                   activation_fn=nn.ReLU, dropout_rate=None,
+                                   activate_final=False)
+  return model
+
+
+def set_in_channels(model, in_channels):
+  """Re-runs the stem swap of perception.py:43-51 for another channel count."""
+  import torch.nn as nn
+  if in_channels == 2:
+    return model
+  feats = model._encoder._model.features
+  tmp = feats._modules['0']._modules['0']
+  feats._modules['0']._modules['0'] = nn.Conv2d(
+      in_channels=in_channels, out_channels=tmp.out_channels,
+      kernel_size=tmp.kernel_size, stride=tmp.stride, padding=tmp.padding,
+      bias=tmp.bias)
+  return model
+
+
+def make_imitative_model(T=4, in_channels=2, seed=0, randomize_bn=True):
+  """Reference ``ImitativeModel`` with seeded weights."""
+  install()
+  import torch
+  from oatomobile.baselines.torch.dim.model import ImitativeModel
+  torch.manual_seed(seed)
+  m = ImitativeModel(output_shape=(T, 2))
+  fix_locscale(m)
+  set_in_channels(m, in_channels)
+  if randomize_bn:
+    randomize_batchnorm(m, seed + 7919)
+  return m.eval()
+
+
+def make_behavioural_model(T=4, in_channels=2, seed=0, randomize_bn=True):
+  install()
+  import torch
+  from oatomobile.baselines.torch.cil.model import BehaviouralModel
+  torch.manual_seed(seed)
+  m = BehaviouralModel(output_shape=(T, 2))
+  set_in_channels(m, in_channels)
+  if randomize_bn:
+    randomize_batchnorm(m, seed + 7919)
+  return m.eval()
+
+
+def randomize_batchnorm(model, seed):
+  """Non-trivial BN statistics/affine so BN-folding bugs show up in goldens."""
+  import torch
+  g = torch.Generator().manual_seed(seed)
+  for mod in model.modules():
+    if isinstance(mod, torch.nn.BatchNorm2d):
+      n = mod.num_features
+      with torch.no_grad():
+        mod.running_mean.copy_(torch.randn(n, generator=g) * 0.1)
+        mod.running_var.copy_(torch.rand(n, generator=g) + 0.5)
+        mod.weight.copy_(torch.rand(n, generator=g) + 0.5)
+        mod.bias.copy_(torch.randn(n, generator=g) * 0.1)
+  return model

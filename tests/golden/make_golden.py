@@ -1,0 +1,188 @@
+"""Generates tests/golden/*.npz by running the REAL reference (OATML/oatomobile,
+/root/reference) on the CPU through oracle/ref_shim.py.
+
+Run in the build container only (`python tests/golden/make_golden.py`); the GPU
+box has no reference tree and only reads the committed vectors.  Inputs and
+weights are NOT stored: they are regenerated from seeds by
+`oatomobile_b200.synthetic` (deterministic CPU generators), loaded into the
+reference modules with `load_state_dict(strict=True)`.
+
+Reference entry points exercised (paths relative to the reference root):
+  ImitativeModel.transform / _params / _goal_likelihood / forward
+                                          oatomobile/baselines/torch/dim/model.py
+  AutoregressiveFlow._forward / _inverse  oatomobile/torch/networks/sequence.py
+  RIPAgent.__call__ (body, lines 59-151)  oatomobile/baselines/torch/rip/agent.py
+  DIMAgent.__call__                       oatomobile/baselines/torch/dim/agent.py
+  BehaviouralModel.forward / CILAgent     oatomobile/baselines/torch/cil/
+Sanctioned deviations: `_locscale` head width 4 for T != 4;
+`model._forward/_inverse` routed to `model._decoder.*` for RIPAgent; stem conv
+rebuilt for in_channels != 2.
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+from oracle import ref_shim  # noqa: E402
+from oatomobile_b200.synthetic import synthetic_inputs, synthetic_state_dict  # noqa: E402
+
+CONFIGS = {
+    # name: (T, C, E, B, K, weight seed base, input seed)
+    "dim_T4_C2": dict(T=4, C=2, E=3, B=2, K=8, wseed=100, iseed=0),
+    "dim_T10_C4": dict(T=10, C=4, E=4, B=2, K=16, wseed=200, iseed=5),
+}
+
+
+def ref_models(cfg):
+  ms = []
+  for m in range(cfg["E"]):
+    model = ref_shim.make_imitative_model(T=cfg["T"], in_channels=cfg["C"], seed=0,
+                                          randomize_bn=False)
+    model.load_state_dict(synthetic_state_dict("dim", cfg["C"], cfg["wseed"] + m), strict=True)
+    ms.append(model.eval())
+  return ms
+
+
+def bypass_agent(cls, **attrs):
+  """Builds a reference agent without CARLA (SetPointAgent.__init__ needs it)."""
+  agent = object.__new__(cls)
+  for k, v in attrs.items():
+    setattr(agent, k, v)
+  return agent
+
+
+def observation(inp, b):
+  """A raw simulator observation for scene b (HWC lidar, xyz goals)."""
+  goal3 = np.concatenate([inp["goal"][b].numpy(), np.zeros((inp["goal"].shape[1], 1))], -1)
+  return {
+      "bird_view_camera_cityscapes": np.zeros((4, 4, 3), np.float32),
+      "lidar": np.ascontiguousarray(inp["lidar"][b].permute(1, 2, 0).numpy()),
+      "velocity": inp["velocity"][b].numpy(),
+      "is_at_traffic_light": int(inp["is_at_traffic_light"][b, 0]),
+      "traffic_light_state": int(inp["traffic_light_state"][b, 0]),
+      "goal": goal3.astype(np.float32),
+  }
+
+
+def make_dim(name, cfg):
+  T, C, E, B, K = cfg["T"], cfg["C"], cfg["E"], cfg["B"], cfg["K"]
+  inp = synthetic_inputs(B, C, K, T, seed=cfg["iseed"])
+  models = ref_models(cfg)
+  out = {}
+  with torch.no_grad():
+    obs = models[0].transform({"lidar": inp["lidar"].clone()})
+    vis = obs["visual_features"].contiguous()
+    out["visual_features"] = vis.numpy()
+    ctx = dict(visual_features=vis, velocity=inp["velocity"],
+               is_at_traffic_light=inp["is_at_traffic_light"],
+               traffic_light_state=inp["traffic_light_state"])
+    zs = [m._params(**ctx) for m in models]
+    out["z"] = torch.stack(zs).numpy()
+    x = inp["x"].reshape(B * K, T, 2)
+    rep = lambda z: z.repeat_interleave(K, dim=0)
+    y, lad_f = models[0]._decoder._forward(x, rep(zs[0]))
+    out["y"] = y.view(B, K, T, 2).numpy()
+    out["fwd_logabsdet"] = lad_f.view(B, K).numpy()
+    q = torch.empty(E, B, K)
+    for m in range(E):
+      xi, lp, lad = models[m]._decoder._inverse(y, rep(zs[m]))
+      q[m] = (lp - lad).view(B, K)
+      if m == 1:
+        out["inv1_x"] = xi.view(B, K, T, 2).numpy()
+        out["inv1_log_prob"] = lp.view(B, K).numpy()
+        out["inv1_logabsdet"] = lad.view(B, K).numpy()
+    out["q_nogoal"] = q.numpy().copy()
+    gl = torch.empty(B, K)
+    y4 = y.view(B, K, T, 2)
+    for b in range(B):
+      for k in range(K):  # per-sample value = batch mean over a batch of one
+        gl[b, k] = models[0]._goal_likelihood(y=y4[b, k][None], goal=inp["goal"][b][None],
+                                              epsilon=1.0)
+    out["goal_ll"] = gl.numpy()
+    out["goal_ll_batchmean_k0"] = models[0]._goal_likelihood(
+        y=y4[:, 0], goal=inp["goal"], epsilon=1.0).numpy()
+    qg = q + gl.unsqueeze(0)
+    out["q"] = qg.numpy()
+    for algo in ("WCM", "BCM", "MA"):  # rip/agent.py:121-127 on per-sample scores
+      if algo == "WCM":
+        s, _ = torch.min(-qg, dim=0)
+      elif algo == "BCM":
+        s, _ = torch.max(-qg, dim=0)
+      else:
+        s = torch.mean(-qg, dim=0)
+      ks = torch.argmin(s, dim=1)
+      out["s_" + algo] = s.numpy()
+      out["kstar_" + algo] = ks.numpy().astype(np.int64)
+      out["plan_" + algo] = y4[torch.arange(B), ks].numpy()
+
+  # ---- gradient planners as written -----------------------------------------
+  # ImitativeModel.forward (dim/model.py:76-141): the initial x is one base sample.
+  for p in models[0].parameters():
+    p.requires_grad_(False)
+  torch.manual_seed(1234)
+  x0 = models[0]._decoder._base_dist.sample().view(1, T, 2)
+  out["dim_forward_x0"] = x0.numpy()
+  torch.manual_seed(1234)
+  plan = models[0].forward(num_steps=10, goal=inp["goal"], lr=1e-1, epsilon=1.0, **ctx)
+  out["dim_forward_goal"] = plan.detach().numpy()
+  torch.manual_seed(1234)
+  plan = models[0].forward(num_steps=10, goal=None, lr=5e-2, epsilon=1.0, **ctx)
+  out["dim_forward_nogoal"] = plan.detach().numpy()
+
+  # RIPAgent.__call__ / DIMAgent.__call__ on scene 0 (rip/agent.py:52-151).
+  from oatomobile.baselines.torch.rip.agent import RIPAgent
+  from oatomobile.baselines.torch.dim.agent import DIMAgent
+  for m in models:
+    for p in m.parameters():
+      p.requires_grad_(False)
+    m._forward = m._decoder._forward  # rip/agent.py:106,111,137 reference missing attrs
+    m._inverse = m._decoder._inverse
+  if T == 4:  # the agents' interpolation assumes 40 // T spacing; both run for any T
+    pass
+  for algo in ("WCM", "BCM", "MA"):
+    agent = bypass_agent(RIPAgent, _algorithm=algo, _models=models,
+                         _device=torch.device("cpu"))
+    out["rip_agent_" + algo] = RIPAgent.__call__(agent, observation(inp, 0))
+  agent = bypass_agent(DIMAgent, _model=models[0], _device=torch.device("cpu"))
+  torch.manual_seed(4321)
+  out["dim_agent_x0"] = models[0]._decoder._base_dist.sample().view(1, T, 2).numpy()
+  torch.manual_seed(4321)
+  out["dim_agent"] = DIMAgent.__call__(agent, observation(inp, 0))
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+  print(name, {k: v.shape for k, v in out.items()})
+
+
+def make_cil():
+  T, C, B = 4, 2, 3
+  inp = synthetic_inputs(B, C, 1, T, seed=9)
+  model = ref_shim.make_behavioural_model(T=T, in_channels=C, seed=0, randomize_bn=False)
+  model.load_state_dict(synthetic_state_dict("cil", C, 300), strict=True)
+  model.eval()
+  mode = torch.tensor([[0.0], [2.0], [3.0]])
+  out = {}
+  with torch.no_grad():
+    vis = model.transform({"lidar": inp["lidar"].clone()})["visual_features"].contiguous()
+    out["plan"] = model(visual_features=vis, velocity=inp["velocity"],
+                        is_at_traffic_light=inp["is_at_traffic_light"],
+                        traffic_light_state=inp["traffic_light_state"], mode=mode).numpy()
+    from oatomobile.baselines.torch.cil.agent import CILAgent
+    agent = bypass_agent(CILAgent, _model=model, _device=torch.device("cpu"))
+    out["cil_agent"] = CILAgent.__call__(agent, observation(inp, 0))
+  np.savez_compressed(os.path.join(HERE, "cil_T4_C2.npz"), **out)
+  print("cil", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+  torch.set_num_threads(8)
+  ref_shim.install()
+  for name, cfg in CONFIGS.items():
+    make_dim(name, cfg)
+  make_cil()

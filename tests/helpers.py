@@ -1,0 +1,49 @@
+"""Shared test helpers: golden loading, seeded fixtures, the parity bar."""
+import os
+
+import numpy as np
+import torch
+
+from oatomobile_b200.synthetic import synthetic_inputs, synthetic_state_dict
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# Must match tests/golden/make_golden.py::CONFIGS.
+GOLDEN_CONFIGS = {
+    "dim_T4_C2": dict(T=4, C=2, E=3, B=2, K=8, wseed=100, iseed=0),
+    "dim_T10_C4": dict(T=10, C=4, E=4, B=2, K=16, wseed=200, iseed=5),
+}
+
+# north_star: "within 1e-4 relative on log-probs and waypoint means"
+REL_TOL = 1e-4
+
+
+def golden(name):
+  return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+
+
+def fixture(cfg):
+  inp = synthetic_inputs(cfg["B"], cfg["C"], cfg["K"], cfg["T"], seed=cfg["iseed"])
+  sds = [synthetic_state_dict("dim", cfg["C"], cfg["wseed"] + m) for m in range(cfg["E"])]
+  return inp, sds
+
+
+def assert_close(actual, expected, tol=REL_TOL, what=""):
+  """|a-b| <= tol * max(|a|,|b|,1) elementwise (SURVEY.md §8(d) parity bar)."""
+  a = torch.as_tensor(np.asarray(actual.detach().cpu() if torch.is_tensor(actual) else actual),
+                      dtype=torch.float64)
+  b = torch.as_tensor(np.asarray(expected.detach().cpu() if torch.is_tensor(expected) else expected),
+                      dtype=torch.float64)
+  assert a.shape == b.shape, "%s: shape %s vs %s" % (what, tuple(a.shape), tuple(b.shape))
+  scale = torch.maximum(torch.maximum(a.abs(), b.abs()), torch.ones_like(a))
+  err = ((a - b).abs() / scale)
+  worst = err.max().item() if err.numel() else 0.0
+  assert worst <= tol, "%s: max rel err %.3e > %.1e" % (what, worst, tol)
+  return worst
+
+
+def top2_gap(s):
+  """Relative gap between the best and second-best score per row."""
+  s = torch.as_tensor(s, dtype=torch.float64)
+  v, _ = torch.sort(s, dim=1)
+  return ((v[:, 1] - v[:, 0]) / torch.clamp(v[:, 0].abs(), min=1.0))
