@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
       sys.stderr.write(out.decode())
     if p.returncode != 0:
       raise RuntimeError("nvcc failed on %s" % src)
-  link = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+  link = [_nvcc(), "-shared", "-cudart", "static", "-o", LIB] + objs
   subprocess.check_call(link)
   return LIB
 

@@ -381,6 +381,7 @@ static int check_device(int want, const char* who) {
 
 int oat_transform_visual(const float* lidar, int32_t B, int32_t C, int32_t H, int32_t W,
                          float* visual, void* stream) {
+  if (B <= 0 || C <= 0) return 0;
   if (!lidar || !visual) return fail("oat_transform_visual: null pointer");
   if (H < 2 || W < 2) return fail("oat_transform_visual: input must be at least 2x2");
   return launch_transform_visual(lidar, B, C, H, W, visual, (cudaStream_t)stream);
@@ -388,8 +389,8 @@ int oat_transform_visual(const float* lidar, int32_t B, int32_t C, int32_t H, in
 
 int oat_encode(OatEnsemble* ens, const float* visual, const float* scalars, int32_t B, float* z,
                void* stream) {
-  if (!ens || !visual || !scalars || !z) return fail("oat_encode: null argument");
   if (B <= 0) return 0;
+  if (!ens || !visual || !scalars || !z) return fail("oat_encode: null argument");
   if (int rc = check_device(ens->device, "oat_encode")) return rc;
   if (int rc = oat_ensemble_reserve(ens, B)) return rc;
   return encoder_forward(ens, visual, scalars, B, z, (cudaStream_t)stream);
@@ -404,6 +405,7 @@ static PtrTable one_model(const OatModel* m) {
 
 int oat_flow_forward(const OatModel* model, const float* x, const float* z, int64_t N, int32_t T,
                      int32_t rows_per_z, float* y, float* logabsdet, void* stream) {
+  if (N <= 0) return 0;
   if (!model || !x || !z || !y) return fail("oat_flow_forward: null argument");
   if (model->kind == OAT_KIND_CIL) return fail("oat_flow_forward: not a flow model");
   if (int rc = check_device(model->device, "oat_flow_forward")) return rc;
@@ -419,6 +421,7 @@ int oat_flow_forward(const OatModel* model, const float* x, const float* z, int6
 int oat_flow_inverse(const OatModel* model, const float* y, const float* z, int64_t N, int32_t T,
                      int32_t rows_per_z, float* x, float* log_prob, float* logabsdet,
                      void* stream) {
+  if (N <= 0) return 0;
   if (!model || !y || !z) return fail("oat_flow_inverse: null argument");
   if (model->kind == OAT_KIND_CIL) return fail("oat_flow_inverse: not a flow model");
   if (int rc = check_device(model->device, "oat_flow_inverse")) return rc;
@@ -434,6 +437,7 @@ int oat_flow_inverse(const OatModel* model, const float* y, const float* z, int6
 int oat_rip_sample_score(OatEnsemble* ens, int32_t proposal_idx, const float* z, const float* x,
                          const float* goal, int32_t G, float epsilon, int32_t B, int32_t K,
                          int32_t T, float* y, float* q, void* stream) {
+  if ((int64_t)B * K <= 0) return 0;
   if (!ens || !z || !y || !q) return fail("oat_rip_sample_score: null argument");
   const int E = (int)ens->models.size();
   if (proposal_idx >= E) return fail("oat_rip_sample_score: proposal_idx out of range");
@@ -466,6 +470,7 @@ int oat_rip_sample_score(OatEnsemble* ens, int32_t proposal_idx, const float* z,
 int oat_rip_aggregate(const float* q, int32_t E, int32_t B, int32_t K, int32_t algo,
                       const float* y, int32_t T, float* s, int32_t* kstar, float* sbest,
                       float* plan, void* stream) {
+  if (B <= 0) return 0;
   if (!q || !kstar) return fail("oat_rip_aggregate: null argument");
   if (plan && !y) return fail("oat_rip_aggregate: plan requested without y");
   return launch_aggregate(q, E, B, K, algo, y, T, s, kstar, sbest, plan, (cudaStream_t)stream);
@@ -473,6 +478,7 @@ int oat_rip_aggregate(const float* q, int32_t E, int32_t B, int32_t K, int32_t a
 
 int oat_cil_rollout(const OatModel* model, const float* z, int32_t B, int32_t T, float* y,
                     void* stream) {
+  if (B <= 0 || T <= 0) return 0;
   if (!model || !z || !y) return fail("oat_cil_rollout: null argument");
   if (model->kind != OAT_KIND_CIL) return fail("oat_cil_rollout: not a BehaviouralModel");
   if (int rc = check_device(model->device, "oat_cil_rollout")) return rc;

@@ -49,6 +49,13 @@ class RIPScorer:
       raise ValueError("ranks other than 0 need `proposal_model` (a replica of global model 0)")
     self._ens = None
     self._ens_key = None
+    self.stage_events = None  # set to a list to record (name, cuda event) marks per call
+
+  def _mark(self, name: str) -> None:
+    if self.stage_events is not None:
+      ev = torch.cuda.Event(enable_timing=True)
+      ev.record()
+      self.stage_events.append((name, ev))
 
   # ---- handles ---------------------------------------------------------------
   def _ensemble(self) -> N.EnsembleHandle:
@@ -74,8 +81,10 @@ class RIPScorer:
             epsilon: float = 1.0, want_s: bool = False) -> Dict[str, torch.Tensor]:
     """z [E_local,B,64], x [B,K,T,2] → plan/kstar/sbest (+ y, q, s)."""
     ens = self._ensemble()
+    self._mark("flow_begin")
     if self._world == 1:
       y, q = ops.rip_sample_score(ens, z, x, goal, epsilon, proposal_idx=0)
+      self._mark("flow_end")
     else:
       import torch.distributed as dist
       # (1) z_0 from the owner of model 0 (64 floats per scene).
@@ -89,12 +98,15 @@ class RIPScorer:
                                 x.reshape(-1, x.shape[2], 2), z0, rows_per_z=x.shape[1])
         y = y.view_as(x)
         _, q = ops.rip_sample_score(ens, z, None, goal, epsilon, proposal_idx=-1, y=y)
+      self._mark("flow_end")
       # (3) the single data-path collective: all-gather of per-model scores.
       q_all = torch.empty(self._world * q.shape[0], q.shape[1], q.shape[2], device=q.device,
                           dtype=q.dtype)
       dist.all_gather_into_tensor(q_all, q.contiguous(), group=self._group)
       q = q_all
+    self._mark("aggregate_begin")
     kstar, sbest, plan, s = ops.rip_aggregate(q, y, self._algorithm, want_s=want_s)
+    self._mark("aggregate_end")
     out = dict(plan=plan, kstar=kstar, sbest=sbest, y=y, q=q)
     if want_s:
       out["s"] = s
@@ -104,10 +116,58 @@ class RIPScorer:
                want_s: bool = False, **context: torch.Tensor) -> Dict[str, torch.Tensor]:
     """Full step of the metric on device-resident inputs.  `context` holds either
     `lidar` [B,C,200,200] (raw) or `visual_features` [B,C,100,100] (transformed)."""
+    self._mark("step_begin")
     if "lidar" in context:
       context = dict(context)
       context["visual_features"] = ops.transform_visual(context.pop("lidar"))
+    self._mark("encode_begin")
     z = self.encode(**context)
+    self._mark("encode_end")
     out = self.score(z, x, goal, epsilon, want_s)
     out["z"] = z
     return out
+
+
+class HostRIPPipeline:
+  """End-to-end call with HOST buffers: pinned-memory inputs are copied to the GPU,
+  scored, and the selected plans copied back — what an agent loop outside the GPU
+  would call once per batch of observations (rip/agent.py:71-74,139 do the same
+  H2D/D2H per tick).  Device and pinned result buffers are allocated once."""
+
+  INPUT_KEYS = ("lidar", "velocity", "is_at_traffic_light", "traffic_light_state", "goal", "x")
+
+  def __init__(self, scorer: RIPScorer, device) -> None:
+    self._scorer = scorer
+    self._device = torch.device(device)
+    self._dev = {}
+    self._host_out = {}
+    self.h2d_bytes = 0
+    self.d2h_bytes = 0
+
+  def __call__(self, host: Dict[str, torch.Tensor], epsilon: float = 1.0):
+    h2d = 0
+    for k in self.INPUT_KEYS:
+      src = host[k]
+      buf = self._dev.get(k)
+      if buf is None or buf.shape != src.shape:
+        buf = torch.empty(src.shape, dtype=torch.float32, device=self._device)
+        self._dev[k] = buf
+      buf.copy_(src, non_blocking=True)  # async H2D from pinned memory on the current stream
+      h2d += src.numel() * 4
+    d = dict(self._dev)
+    x, goal = d.pop("x"), d.pop("goal")
+    out = self._scorer(x=x, goal=goal, epsilon=epsilon, **d)
+    d2h = 0
+    res = {}
+    for k in ("plan", "kstar", "sbest"):
+      t = out[k]
+      hb = self._host_out.get(k)
+      if hb is None or hb.shape != t.shape:
+        hb = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        self._host_out[k] = hb
+      hb.copy_(t, non_blocking=True)
+      d2h += t.numel() * t.element_size()
+      res[k] = hb
+    torch.cuda.current_stream(self._device).synchronize()  # results are now valid on the host
+    self.h2d_bytes, self.d2h_bytes = h2d, d2h
+    return res
