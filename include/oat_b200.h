@@ -73,6 +73,15 @@ OAT_API int oat_ensemble_create(OatModel* const* models, int32_t num_models, Oat
 OAT_API int oat_ensemble_destroy(OatEnsemble* ens);
 OAT_API int oat_ensemble_reserve(OatEnsemble* ens, int32_t batch);
 
+/* Selects the kernel family of the 34 pointwise convolutions + classifier:
+ * 1 = tcgen05/TMA tensor-core GEMM with 3xTF32 error compensation (default),
+ * 0 = FP32 SIMT GEMM.  Both meet the 1e-4 parity bar; see DESIGN.md. */
+OAT_API int oat_ensemble_set_pw_impl(OatEnsemble* ens, int32_t impl);
+
+/* Selects the flow kernel family process-wide: 1 = tcgen05 3xTF32 recurrent GEMMs
+ * with the state resident in shared/tensor memory (default), 0 = FP32 SIMT.        */
+OAT_API int oat_set_flow_impl(int32_t impl);
+
 /* transforms.downsample_visual_features + transpose_visual_features
  * (oatomobile/torch/transforms.py:34-49, called from dim/model.py:245-251):
  * lidar [B,C,H,W] -> visual [B,C,100,100], bilinear align_corners=True then H<->W. */
@@ -121,6 +130,13 @@ OAT_API int oat_rip_aggregate(const float* q, int32_t E, int32_t B, int32_t K, i
  * z [B,64] -> y [B,T,2].                                                          */
 OAT_API int oat_cil_rollout(const OatModel* model, const float* z, int32_t B, int32_t T,
                     float* y, void* stream);
+
+/* TEST HOOK (tests/test_gpu_tc_gemm.py): one grouped pointwise GEMM on the tensor
+ * cores, C[e,m,n] = act(sum_k A[e,m,k] W[e,n,k] + bias[e,n]) (+ R).  Allocates and
+ * frees its TF32-split weight copies; synchronises the stream.                   */
+OAT_API int oat_debug_tc_gemm(const float* A, const float* W, const float* bias, const float* R,
+                      float* C, int32_t M, int32_t K, int32_t N, int32_t E, int32_t relu6,
+                      void* stream);
 
 /* Number of kernel launches issued by this library since load (bench.py's
  * `gpu_launches`). */

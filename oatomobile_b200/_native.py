@@ -22,7 +22,8 @@ SYMBOLS = (
     "oat_model_in_channels", "oat_ensemble_create", "oat_ensemble_destroy",
     "oat_ensemble_reserve", "oat_transform_visual", "oat_encode", "oat_flow_forward",
     "oat_flow_inverse", "oat_rip_sample_score", "oat_rip_aggregate", "oat_cil_rollout",
-    "oat_launch_count",
+    "oat_launch_count", "oat_ensemble_set_pw_impl", "oat_debug_tc_gemm",
+    "oat_set_flow_impl",
 )
 
 
@@ -73,6 +74,9 @@ def lib() -> ctypes.CDLL:
     L.oat_rip_aggregate.argtypes = [vp, c_i32, c_i32, c_i32, c_i32, vp, c_i32, vp, vp, vp, vp,
                                     vp]
     L.oat_cil_rollout.argtypes = [vp, vp, c_i32, c_i32, vp, vp]
+    L.oat_ensemble_set_pw_impl.argtypes = [vp, c_i32]
+    L.oat_set_flow_impl.argtypes = [c_i32]
+    L.oat_debug_tc_gemm.argtypes = [vp, vp, vp, vp, vp, c_i32, c_i32, c_i32, c_i32, c_i32, vp]
     for name in SYMBOLS:
       fn = getattr(L, name, None)
       if fn is not None and name not in ("oat_last_error", "oat_launch_count"):
@@ -84,6 +88,21 @@ def lib() -> ctypes.CDLL:
 def check(rc: int) -> None:
   if rc != 0:
     raise NativeLibraryError(lib().oat_last_error().decode() or "native call failed")
+
+
+_default_pw_impl = "tcgen05"
+
+
+def set_default_pw_impl(impl: str) -> None:
+  """Kernel family new ensembles use for the pointwise convolutions ("tcgen05"|"simt")."""
+  global _default_pw_impl
+  assert impl in ("tcgen05", "simt")
+  _default_pw_impl = impl
+
+
+def set_flow_impl(impl: str) -> None:
+  """"tcgen05" (default) or "simt": kernel family of the autoregressive flow."""
+  check(lib().oat_set_flow_impl({"simt": 0, "tcgen05": 1}[impl]))
 
 
 def launch_count() -> int:
@@ -158,9 +177,15 @@ class EnsembleHandle:
     check(L.oat_ensemble_create(arr, len(models), ctypes.byref(out)))
     self.ptr = out
     self.device = models[0].device
+    if _default_pw_impl != "tcgen05":
+      self.set_pw_impl(_default_pw_impl)
 
   def __len__(self):
     return len(self.models)
+
+  def set_pw_impl(self, impl: str) -> None:
+    """"tcgen05" (3xTF32 tensor-core GEMMs, default) or "simt" (FP32 FFMA GEMMs)."""
+    check(lib().oat_ensemble_set_pw_impl(self.ptr, {"simt": 0, "tcgen05": 1}[impl]))
 
   def __deepcopy__(self, memo):
     return None

@@ -11,11 +11,13 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace oat {
 
 static thread_local std::string g_error;
 int64_t g_launch_count = 0;
+int g_flow_impl = 1;
 
 void set_error(const std::string& msg) { g_error = msg; }
 int fail(const std::string& msg) {
@@ -261,6 +263,12 @@ int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind
     }
   }
 
+  Off flow_tc{0, 0};
+  if (kind != OAT_KIND_CIL) {
+    flow_tc.w = P.alloc(kFlowTcFloats);
+    pack_flow_tc_image(P.arena.data() + flow.w, P.arena.data() + flow_tc.w);
+  }
+
   // ---- upload
   OatModel* m = new OatModel();
   m->kind = kind;
@@ -300,6 +308,7 @@ int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind
   m->fc = dev(fc);
   for (int i = 0; i < 3; ++i) m->merger[i] = dev(mg[i]);
   m->flow = m->arena + flow.w;
+  m->flow_tc = (kind != OAT_KIND_CIL) ? m->arena + flow_tc.w : nullptr;
   *out = m;
   return 0;
 }
@@ -328,13 +337,98 @@ int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble
     e->models.push_back(models[i]);
   }
   e->device = models[0]->device;
+  // ---- tensor-core copies of every pointwise layer: [E][N][K], TF32 hi/lo split ----
+  {
+    const OatModel* m0 = models[0];
+    struct L { int K, N; };
+    std::vector<L> layers;
+    for (const BlockW& b : m0->blocks) {
+      if (b.hid != b.cin) layers.push_back({b.cin, b.hid});
+      layers.push_back({b.hid, b.cout});
+    }
+    layers.push_back({320, 1280});
+    layers.push_back({1280, OAT_ENC_FEATURES});
+    size_t total = 0;
+    for (const L& l : layers) total += (size_t)num_models * (2 * (size_t)l.K * l.N + l.N);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(e->device);
+    cudaError_t err = cudaMalloc(&e->tc_arena, total * sizeof(float));
+    if (err != cudaSuccess) {
+      cudaSetDevice(prev);
+      delete e;
+      return fail(std::string("oat_ensemble_create: ") + cudaGetErrorString(err));
+    }
+    float* p = e->tc_arena;
+    int rc = 0;
+    for (size_t li = 0; li < layers.size() && rc == 0; ++li) {
+      TcLayer t;
+      t.K = layers[li].K; t.N = layers[li].N;
+      const size_t kn = (size_t)t.K * t.N;
+      t.wh = p; p += kn * num_models;
+      t.wl = p; p += kn * num_models;
+      t.bias = p; p += (size_t)t.N * num_models;
+      for (int mi = 0; mi < num_models && rc == 0; ++mi) {
+        const OatModel* m = models[mi];
+        // walk the same order as `layers`
+        const ConvW* cw = nullptr;
+        size_t idx = 0;
+        for (const BlockW& b : m->blocks) {
+          if (b.hid != b.cin) { if (idx == li) cw = &b.expand; ++idx; }
+          if (idx == li) cw = &b.project;
+          ++idx;
+          if (cw) break;
+        }
+        if (!cw) cw = (li == layers.size() - 2) ? &m->last : &m->fc;
+        rc = tc_pack_weights(cw->w, t.K, t.N, t.wh + kn * mi, t.wl + kn * mi, 0);
+        if (rc == 0 && cudaMemcpy(t.bias + (size_t)t.N * mi, cw->b, t.N * sizeof(float),
+                                  cudaMemcpyDeviceToDevice) != cudaSuccess)
+          rc = fail("oat_ensemble_create: bias copy failed");
+      }
+      e->tc.push_back(t);
+    }
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) rc = fail("oat_ensemble_create: pack failed");
+    cudaSetDevice(prev);
+    if (rc != 0) {
+      cudaFree(e->tc_arena);
+      delete e;
+      return rc;
+    }
+  }
   *out = e;
   return 0;
+}
+
+int oat_ensemble_set_pw_impl(OatEnsemble* ens, int32_t impl) {
+  if (!ens) return fail("oat_ensemble_set_pw_impl: null ensemble");
+  if (impl != 0 && impl != 1) return fail("oat_ensemble_set_pw_impl: impl must be 0 (simt) or 1 (tcgen05)");
+  ens->pw_impl = impl;
+  return 0;
+}
+
+int oat_debug_tc_gemm(const float* A, const float* W, const float* bias, const float* R, float* C,
+                      int32_t M, int32_t K, int32_t N, int32_t E, int32_t relu6, void* stream) {
+  if (!A || !W || !bias || !C) return fail("oat_debug_tc_gemm: null argument");
+  const int64_t n = (int64_t)E * N * K;
+  float* tmp = nullptr;
+  OAT_CUDA(cudaMalloc(&tmp, 2 * n * sizeof(float)));
+  int rc = tc_split_weights(W, tmp, tmp + n, n, (cudaStream_t)stream);
+  if (rc == 0) {
+    TcGemmProblem p;
+    p.A = A; p.Wh = tmp; p.Wl = tmp + n; p.bias = bias; p.R = R; p.C = C;
+    p.M = M; p.K = K; p.N = N; p.E = E; p.relu6 = relu6;
+    rc = tc_pw_gemm(p, (cudaStream_t)stream);
+  }
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(tmp);
+  if (rc == 0 && e != cudaSuccess) return fail(std::string("oat_debug_tc_gemm: ") + cudaGetErrorString(e));
+  return rc;
 }
 
 int oat_ensemble_destroy(OatEnsemble* ens) {
   if (!ens) return 0;
   if (ens->ws) cudaFree(ens->ws);
+  if (ens->tc_arena) cudaFree(ens->tc_arena);
   delete ens;
   return 0;
 }
@@ -399,8 +493,18 @@ int oat_encode(OatEnsemble* ens, const float* visual, const float* scalars, int3
 static PtrTable one_model(const OatModel* m) {
   PtrTable t;
   for (int i = 0; i < kMaxModels; ++i) t.p[i] = nullptr;
-  t.p[0] = m->flow;
+  t.p[0] = (g_flow_impl == 1 && m->flow_tc) ? m->flow_tc : m->flow;
   return t;
+}
+
+static int dispatch_flow(const FlowLaunch& a, cudaStream_t stream) {
+  return (g_flow_impl == 1 && a.mode != 2) ? launch_flow_tc(a, stream) : launch_flow(a, stream);
+}
+
+int oat_set_flow_impl(int32_t impl) {
+  if (impl != 0 && impl != 1) return fail("oat_set_flow_impl: impl must be 0 (simt) or 1 (tcgen05)");
+  g_flow_impl = impl;
+  return 0;
 }
 
 int oat_flow_forward(const OatModel* model, const float* x, const float* z, int64_t N, int32_t T,
@@ -415,7 +519,7 @@ int oat_flow_forward(const OatModel* model, const float* x, const float* z, int6
   a.logprob = nullptr; a.logabsdet = logabsdet; a.q = nullptr; a.out_model_stride = 0;
   a.goal = nullptr; a.G = 0; a.epsilon = 1.0f; a.N = N; a.T = T; a.rows_per_z = rows_per_z;
   a.skip_model = -1;
-  return launch_flow(a, (cudaStream_t)stream);
+  return dispatch_flow(a, (cudaStream_t)stream);
 }
 
 int oat_flow_inverse(const OatModel* model, const float* y, const float* z, int64_t N, int32_t T,
@@ -431,7 +535,7 @@ int oat_flow_inverse(const OatModel* model, const float* y, const float* z, int6
   a.logprob = log_prob; a.logabsdet = logabsdet; a.q = nullptr; a.out_model_stride = 0;
   a.goal = nullptr; a.G = 0; a.epsilon = 1.0f; a.N = N; a.T = T; a.rows_per_z = rows_per_z;
   a.skip_model = -1;
-  return launch_flow(a, (cudaStream_t)stream);
+  return dispatch_flow(a, (cudaStream_t)stream);
 }
 
 int oat_rip_sample_score(OatEnsemble* ens, int32_t proposal_idx, const float* z, const float* x,
@@ -456,15 +560,16 @@ int oat_rip_sample_score(OatEnsemble* ens, int32_t proposal_idx, const float* z,
     a.mode = 0; a.num_models = 1; a.weights = one_model(ens->models[proposal_idx]);
     a.in = x; a.z = z + (int64_t)proposal_idx * B * kHidden; a.z_model_stride = 0;
     a.out = y; a.q = q + (int64_t)proposal_idx * N; a.out_model_stride = 0; a.skip_model = -1;
-    if (int rc = launch_flow(a, (cudaStream_t)stream)) return rc;
+    if (int rc = dispatch_flow(a, (cudaStream_t)stream)) return rc;
     if (E == 1) return 0;
   }
   // scores under every (other) local model (rip/agent.py:109-119)
   a.mode = 1; a.num_models = E;
-  for (int i = 0; i < kMaxModels; ++i) a.weights.p[i] = i < E ? ens->models[i]->flow : nullptr;
+  for (int i = 0; i < kMaxModels; ++i)
+    a.weights.p[i] = i < E ? (g_flow_impl == 1 ? ens->models[i]->flow_tc : ens->models[i]->flow) : nullptr;
   a.in = y; a.z = z; a.z_model_stride = (int64_t)B * kHidden;
   a.out = nullptr; a.q = q; a.out_model_stride = N; a.skip_model = proposal_idx;
-  return launch_flow(a, (cudaStream_t)stream);
+  return dispatch_flow(a, (cudaStream_t)stream);
 }
 
 int oat_rip_aggregate(const float* q, int32_t E, int32_t B, int32_t K, int32_t algo,

@@ -50,6 +50,9 @@ constexpr int kFlowW2 = kFlowB1 + 32;
 constexpr int kFlowB2 = kFlowW2 + 4 * 32;
 constexpr int kFlowFloats = kFlowB2 + 4;  // 15268 (multiple of 4)
 static_assert(kFlowFloats % 4 == 0, "flow weight image must be float4-copyable");
+// Tensor-core flow image (flow_tc.cu): W_hh / W_1 split into TF32 hi/lo parts and
+// pre-swizzled into the K-major SWIZZLE_128B UMMA layout, + gate/head parameters.
+constexpr int kFlowTcFloats = 29604;
 
 // ---- encoder layer descriptors (device pointers into one weight arena) ------
 struct ConvW {
@@ -78,10 +81,23 @@ struct OatModel {
   oat::ConvW fc;                    // 1280 -> 128
   oat::ConvW merger[3];             // [in][64] transposed
   const float* flow = nullptr;      // kFlowFloats
+  const float* flow_tc = nullptr;   // kFlowTcFloats (null for CIL)
 };
+
+namespace oat {
+struct TcLayer {  // one pointwise layer of the whole ensemble, tensor-core layout
+  float* wh = nullptr;    // [E][N][K] TF32-exact high parts
+  float* wl = nullptr;    // [E][N][K] low parts
+  float* bias = nullptr;  // [E][N]
+  int K = 0, N = 0;
+};
+}  // namespace oat
 
 struct OatEnsemble {
   std::vector<OatModel*> models;
+  std::vector<oat::TcLayer> tc;  // pointwise layers in execution order (+ last, fc)
+  float* tc_arena = nullptr;
+  int pw_impl = 1;               // 1 = tcgen05 3xTF32 (default), 0 = FP32 SIMT
   int device = 0;
   int reserved_batch = 0;
   float* ws = nullptr;  // activation workspace
@@ -118,6 +134,9 @@ struct FlowLaunch {
   int skip_model;             // grid.y index that exits immediately (-1: none)
 };
 int launch_flow(const FlowLaunch& a, cudaStream_t stream);
+int launch_flow_tc(const FlowLaunch& a, cudaStream_t stream);  // weights = flow_tc images
+void pack_flow_tc_image(const float* flow_weights, float* image);
+extern int g_flow_impl;  // 1 = tcgen05 (default), 0 = FP32 SIMT
 
 int launch_aggregate(const float* q, int E, int B, int K, int algo, const float* y, int T,
                      float* s, int32_t* kstar, float* sbest, float* plan,

@@ -10,6 +10,7 @@
 // pointwise convolutions are [M=B*H*W, K] x [K, N] GEMMs with a fused
 // bias(+BN) / ReLU6 / residual epilogue.
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace oat {
 namespace {
@@ -222,7 +223,13 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const __grid_constant__ Pw
   }
 }
 
-int launch_pw(const PwArgs& a, int E, cudaStream_t stream) {
+int launch_pw(const PwArgs& a, int E, cudaStream_t stream, const TcLayer* tc = nullptr) {
+  if (tc != nullptr) {  // tcgen05 / TMA path (3xTF32)
+    TcGemmProblem p;
+    p.A = a.A; p.Wh = tc->wh; p.Wl = tc->wl; p.bias = tc->bias; p.R = a.R; p.C = a.C;
+    p.M = a.M; p.K = a.K; p.N = a.N; p.E = E; p.relu6 = a.relu6;
+    return tc_pw_gemm(p, stream);
+  }
   if (a.K % 8 != 0 || a.N % 4 != 0) return fail("pw_gemm: K must be a multiple of 8, N of 4");
   if (a.N <= 16) {
     dim3 grid((a.M + 255) / 256, (a.N + 15) / 16, E);
@@ -368,6 +375,12 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
   }
   float* x = ens->bufA;
   float* y = ens->bufB;
+  size_t li = 0;  // index into ens->tc (pointwise layers in execution order)
+  auto tc = [&]() -> const TcLayer* {
+    const TcLayer* t = ens->pw_impl == 1 ? &ens->tc[li] : nullptr;
+    ++li;
+    return t;
+  };
   for (size_t bi = 0; bi < m0->blocks.size(); ++bi) {
     const BlockW& blk = m0->blocks[bi];
     const int Min = B * blk.hin * blk.hin, Mout = B * blk.hout * blk.hout;
@@ -379,7 +392,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       a.A = x; a.C = ens->bufH1; a.R = nullptr;
       a.a_stride = (int64_t)Min * blk.cin; a.c_stride = (int64_t)Min * blk.hid;
       a.M = Min; a.K = blk.cin; a.N = blk.hid; a.relu6 = 1;
-      if (int rc = launch_pw(a, E, stream)) return rc;
+      if (int rc = launch_pw(a, E, stream, tc())) return rc;
       dw_in = ens->bufH1;
     }
     {  // depthwise 3x3 + BN + ReLU6
@@ -398,7 +411,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       a.A = ens->bufH2; a.C = y; a.R = blk.residual ? x : nullptr;
       a.a_stride = (int64_t)Mout * blk.hid; a.c_stride = (int64_t)Mout * blk.cout;
       a.M = Mout; a.K = blk.hid; a.N = blk.cout; a.relu6 = 0;
-      if (int rc = launch_pw(a, E, stream)) return rc;
+      if (int rc = launch_pw(a, E, stream, tc())) return rc;
     }
     float* t = x; x = y; y = t;
   }
@@ -411,7 +424,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
     a.A = x; a.C = ens->bufH1; a.R = nullptr;
     a.a_stride = (int64_t)B * P * 320; a.c_stride = (int64_t)B * P * 1280;
     a.M = B * P; a.K = 320; a.N = 1280; a.relu6 = 1;
-    if (int rc = launch_pw(a, E, stream)) return rc;
+    if (int rc = launch_pw(a, E, stream, tc())) return rc;
   }
   {  // global average pool -> pooled [E][B][1280]
     const int64_t rows = (int64_t)E * B;
@@ -426,7 +439,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
     a.A = ens->pooled; a.C = ens->feat; a.R = nullptr;
     a.a_stride = (int64_t)B * 1280; a.c_stride = (int64_t)B * 128;
     a.M = B; a.K = 1280; a.N = 128; a.relu6 = 0;
-    if (int rc = launch_pw(a, E, stream)) return rc;
+    if (int rc = launch_pw(a, E, stream, tc())) return rc;
   }
   {  // merger MLP -> z [E][B][64]
     MergerArgs a;

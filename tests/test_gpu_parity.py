@@ -12,6 +12,18 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["tcgen05", "simt"])
+def kernel_family(request):
+  """Every parity test runs on both kernel families: the tcgen05/TMA 3xTF32 path
+  (default) and the FP32 SIMT path."""
+  from oatomobile_b200 import _native
+  _native.set_flow_impl(request.param)
+  _native.set_default_pw_impl(request.param)
+  yield request.param
+  _native.set_flow_impl("tcgen05")
+  _native.set_default_pw_impl("tcgen05")
+
+
 def _models(cfg, sds):
   import oatomobile_b200 as ob
   ms = []
