@@ -246,41 +246,72 @@ int launch_pw(const PwArgs& a, int E, cudaStream_t stream, const TcLayer* tc = n
 }
 
 // ---------------------------------------------------------------------------
-// depthwise 3x3 (pad 1, stride 1|2) + folded BN + ReLU6, NHWC, float4 channels.
+// depthwise 3x3 (pad 1, stride 1|2) + folded BN + ReLU6, NHWC.
+// One thread = 4 channels (float4) x one whole output row: the 9 taps stay in
+// registers and the 3x3 window slides along W, so each output costs 3 (stride 1)
+// or 6 (stride 2) 16-byte loads instead of 9 + 9 weight loads.  HBM-bound.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dw_kernel(const __grid_constant__ PtrTable w,
+__device__ __forceinline__ float4 fma4(const float4 v, const float4 k, const float4 acc) {
+  return make_float4(fmaf(v.x, k.x, acc.x), fmaf(v.y, k.y, acc.y), fmaf(v.z, k.z, acc.z),
+                     fmaf(v.w, k.w, acc.w));
+}
+
+template <int STRIDE>
+__global__ void __launch_bounds__(128) dw_kernel(const __grid_constant__ PtrTable w,
                                                  const __grid_constant__ PtrTable bias,
                                                  const float* __restrict__ in,
                                                  float* __restrict__ out, int B, int Hin,
-                                                 int Hout, int C, int stride) {
+                                                 int Hout, int C) {
   const int model = blockIdx.y;
   const int C4 = C >> 2;
-  const int64_t total = (int64_t)B * Hout * Hout * C4;
+  const int64_t total = (int64_t)B * Hout * C4;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c4 = (int)(idx % C4);
-  const int64_t p = idx / C4;
-  const int ow = (int)(p % Hout), oh = (int)((p / Hout) % Hout);
-  const int64_t b = p / ((int64_t)Hout * Hout);
-  const float* __restrict__ wm = w.p[model];
-  const float* __restrict__ src = in + ((int64_t)model * B + b) * Hin * Hin * C;
-  float4 acc = __ldg(reinterpret_cast<const float4*>(bias.p[model] + 4 * c4));
+  const int oh = (int)((idx / C4) % Hout);
+  const int64_t b = idx / ((int64_t)C4 * Hout);
+  const float* __restrict__ wm = w.p[model] + 4 * c4;
+  float4 k[9];
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    const int ih = oh * stride - 1 + kh;
-    if (ih < 0 || ih >= Hin) continue;
+  for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(wm + t * C));
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias.p[model] + 4 * c4));
+  const float* __restrict__ src = in + ((int64_t)model * B + b) * Hin * Hin * C + 4 * c4;
+  float* __restrict__ dst = out + (((int64_t)model * B + b) * Hout + oh) * Hout * C + 4 * c4;
+  const int ih0 = oh * STRIDE - 1;
+  const bool rv[3] = {ih0 >= 0, true, ih0 + 2 < Hin};
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto ldcol = [&](int iw, float4 (&col)[3]) {
+    const bool cv = iw >= 0 && iw < Hin;
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int iw = ow * stride - 1 + kw;
-      if (iw < 0 || iw >= Hin) continue;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)ih * Hin + iw) * C + 4 * c4));
-      const float4 k = __ldg(reinterpret_cast<const float4*>(wm + (kh * 3 + kw) * C + 4 * c4));
-      acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y);
-      acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+    for (int r = 0; r < 3; ++r)
+      col[r] = (cv && rv[r])
+                   ? __ldg(reinterpret_cast<const float4*>(src + ((int64_t)(ih0 + r) * Hin + iw) * C))
+                   : zero;
+  };
+  float4 L[3], M[3], R[3];
+  ldcol(-1, L);  // left padding column
+  if (STRIDE == 1) ldcol(0, M);
+  for (int ow = 0; ow < Hout; ++ow) {
+    if (STRIDE == 1) {
+      ldcol(ow + 1, R);
+    } else {
+      ldcol(2 * ow, M);
+      ldcol(2 * ow + 1, R);
+    }
+    float4 acc = bv;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      acc = fma4(L[r], k[3 * r + 0], acc);
+      acc = fma4(M[r], k[3 * r + 1], acc);
+      acc = fma4(R[r], k[3 * r + 2], acc);
+    }
+    acc.x = relu6f(acc.x); acc.y = relu6f(acc.y); acc.z = relu6f(acc.z); acc.w = relu6f(acc.w);
+    *reinterpret_cast<float4*>(dst + (int64_t)ow * C) = acc;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      if (STRIDE == 1) { L[r] = M[r]; M[r] = R[r]; } else { L[r] = R[r]; }
     }
   }
-  acc.x = relu6f(acc.x); acc.y = relu6f(acc.y); acc.z = relu6f(acc.z); acc.w = relu6f(acc.w);
-  *reinterpret_cast<float4*>(out + (((int64_t)model * B + b) * Hout * Hout + (int64_t)oh * Hout + ow) * C + 4 * c4) = acc;
 }
 
 // ---------------------------------------------------------------------------
@@ -398,10 +429,12 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
     {  // depthwise 3x3 + BN + ReLU6
       PtrTable w = table([bi](const OatModel* m) { return m->blocks[bi].dw.w; });
       PtrTable b = table([bi](const OatModel* m) { return m->blocks[bi].dw.b; });
-      const int64_t total = (int64_t)Mout * (blk.hid / 4);
-      dim3 grid((unsigned)((total + 255) / 256), E);
-      dw_kernel<<<grid, 256, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid,
-                                         blk.stride);
+      const int64_t total = (int64_t)B * blk.hout * (blk.hid / 4);
+      dim3 grid((unsigned)((total + 127) / 128), E);
+      if (blk.stride == 1)
+        dw_kernel<1><<<grid, 128, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid);
+      else
+        dw_kernel<2><<<grid, 128, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid);
       OAT_LAUNCH_CHECK();
     }
     {  // project 1x1 + BN (linear) + residual

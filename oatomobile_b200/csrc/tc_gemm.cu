@@ -27,10 +27,12 @@
 //   warp 9   MMA issuer: one elected thread issues 3 tcgen05.mma.kind::tf32 per
 //            8-wide k-slice into a TMEM accumulator (128 lanes x BN columns fp32),
 //            tcgen05.commit releases smem stages / publishes the accumulator;
-//   warps0-3 epilogue: tcgen05.ld 32x32b (one output row per thread), folded-BN
-//            bias, ReLU6, residual, 64-byte vector stores.  Two TMEM accumulator
-//            buffers (2 x 256 columns) overlap the epilogue of tile i with the
-//            main loop of tile i+1.
+//   warps0-3 epilogue: tcgen05.ld 32x32b (one output row per thread), RN sum of the
+//            partial accumulators, folded-BN bias, ReLU6, residual; 32-column slabs
+//            are staged in 128B-swizzled shared memory and written with TMA stores
+//            (cp.async.bulk.tensor, double-buffered), which also clip the M/N tails.
+//            When TMEM allows, two accumulator groups overlap the epilogue of tile i
+//            with the main loop of tile i+1.
 #include <cuda.h>
 
 #include <map>
@@ -53,6 +55,7 @@ struct TcArgs {
   CUtensorMap mapA;   // {K, M, E}, box {32, 128, 1}
   CUtensorMap mapWh;  // {K, N, E}, box {32, BN, 1}
   CUtensorMap mapWl;
+  CUtensorMap mapC;   // {N, M, E}, box {32, 128, 1} (store)
   const float* bias;  // [E][N]
   const float* R;     // [E][M][N] or null
   float* C;           // [E][M][N]
@@ -100,6 +103,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)),
       "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1,
+                                             int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+          reinterpret_cast<uint64_t>(map)),
+      "r"(c0), "r"(c1), "r"(c2), "r"(src)
+      : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -157,6 +169,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
   auto sAl = [&](int s) { return sA(s) + TC_A_BYTES; };
   auto sWh = [&](int s) { return sA(s) + 2u * TC_A_BYTES; };
   auto sWl = [&](int s) { return sWh(s) + w_bytes; };
+  const uint32_t stage_out = smem_base + (uint32_t)S * stage_bytes;  // 2 x 16 KB store staging
   auto bar_full = [&](int s) { return smem_u32(&bars[s]); };
   auto bar_split = [&](int s) { return smem_u32(&bars[TC_MAX_STAGES + s]); };
   auto bar_empty = [&](int s) { return smem_u32(&bars[2 * TC_MAX_STAGES + s]); };
@@ -186,6 +199,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapWh)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapWl)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapC)) : "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -286,9 +300,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
     }
   } else {
     // ===================== epilogue (warps 0-3: TMEM lanes 32*warp..) =====================
-    uint32_t lt = 0;
+    uint32_t lt = 0, slab_it = 0;
     const int C = a.chunks;
     const int used = k_blocks < C ? k_blocks : C;  // main accumulators actually written
+    const int et = threadIdx.x;                    // 0..127
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
       const int e = t / tiles_per_model, r = t % tiles_per_model;
       const int m0 = (r / a.n_tiles) * TC_BM, n0 = (r % a.n_tiles) * BN;
@@ -296,43 +311,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
       const uint32_t aph = (a.nbuf == 2) ? ((lt >> 1) & 1) : (lt & 1);
       mbar_wait(bar_tfull(ab), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row = m0 + warp * 32 + lane;
+      const int rrow_i = warp * 32 + lane;         // row inside the tile = TMEM lane
+      const int row = m0 + rrow_i;
       const bool row_ok = row < a.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * (C + 1) * BN);
       const float* __restrict__ bias = a.bias + (int64_t)e * a.N;
-      float* __restrict__ crow = a.C + ((int64_t)e * a.M + row) * a.N;
-      const float* __restrict__ rrow = a.R ? a.R + ((int64_t)e * a.M + row) * a.N : nullptr;
-      for (int c = 0; c < BN; c += 16) {
-        float v[16], u[16];
-        tmem_ld16(taddr + (uint32_t)c, v);  // warp-wide: executed by all 32 lanes
-        for (int j = 1; j < used; ++j) {    // partial main products, round-to-nearest adds
-          tmem_ld16(taddr + (uint32_t)(j * BN + c), u);
+      const float* __restrict__ rrow = (a.R && row_ok) ? a.R + ((int64_t)e * a.M + row) * a.N : nullptr;
+      for (int c0 = 0; c0 < BN; c0 += 32, ++slab_it) {
+        const uint32_t sbuf = stage_out + (slab_it & 1) * (uint32_t)TC_A_BYTES;
+        // the TMA store that last read this staging buffer (2 slabs ago) must have drained
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {
+          const int c = c0 + hc * 16;
+          float v[16], u[16];
+          tmem_ld16(taddr + (uint32_t)c, v);  // warp-wide: executed by all 32 lanes
+          for (int j = 1; j < used; ++j) {    // partial main products, round-to-nearest adds
+            tmem_ld16(taddr + (uint32_t)(j * BN + c), u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += u[i];
+          }
+          tmem_ld16(taddr + (uint32_t)(C * BN + c), u);  // correction terms
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += u[i];
-        }
-        tmem_ld16(taddr + (uint32_t)(C * BN + c), u);  // correction terms
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += u[i];
-        const int n = n0 + c;
-        if (row_ok && n < a.N) {  // N is a multiple of 4, so float4 groups are all-or-nothing
+          const int n = n0 + c;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            if (n + j < a.N) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (n + j < a.N) {  // N is a multiple of 4: float4 groups are all-or-nothing
               const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n + j));
-              float4 o = make_float4(v[j] + b.x, v[j + 1] + b.y, v[j + 2] + b.z, v[j + 3] + b.w);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
               if (a.relu6) { o.x = relu6f(o.x); o.y = relu6f(o.y); o.z = relu6f(o.z); o.w = relu6f(o.w); }
               if (rrow) {
                 const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + n + j));
                 o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
               }
-              *reinterpret_cast<float4*>(crow + n + j) = o;
             }
+            // staging tile [128 rows][32 floats], 128B swizzle: 16B chunk index ^= row % 8
+            const uint32_t chunk = (uint32_t)(hc * 4 + (j >> 2));
+            const uint32_t dst = sbuf + (uint32_t)rrow_i * 128u + ((chunk ^ (uint32_t)(rrow_i & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(o.x), "f"(o.y),
+                         "f"(o.z), "f"(o.w)
+                         : "memory");
           }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (et == 0 && n0 + c0 < a.N) tma_store_3d(&a.mapC, sbuf, n0 + c0, m0, e);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar_tempty(ab));
     }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -428,20 +459,22 @@ int tc_pw_gemm(const TcGemmProblem& p, cudaStream_t stream) {
   a.chunks = (p.K + 199) / 200;
   if (a.chunks > 7) a.chunks = 7;
   const int sets = a.chunks + 1;                       // + correction buffer
-  const int bn_max = ((TC_TMEM_COLS / sets) / 16) * 16;  // (C+1)*BN <= 512 TMEM columns
+  int bn_max = ((TC_TMEM_COLS / sets) / 32) * 32;  // (C+1)*BN <= 512 TMEM columns
+  if (bn_max > 224) bn_max = 224;                  // two smem stages + store staging must fit
   a.n_tiles = (p.N + bn_max - 1) / bn_max;
   const int per = (p.N + a.n_tiles - 1) / a.n_tiles;
-  a.BN = ((per + 15) / 16) * 16;
+  a.BN = ((per + 31) / 32) * 32;  // whole 32-column store slabs
   a.nbuf = (2 * sets * a.BN <= TC_TMEM_COLS) ? 2 : 1;
   a.m_tiles = (p.M + TC_BM - 1) / TC_BM;
   const int stage_bytes = 2 * TC_A_BYTES + 2 * a.BN * 128;
-  a.stages = (216 * 1024) / stage_bytes;
+  a.stages = (216 * 1024 - 2 * TC_A_BYTES) / stage_bytes;  // minus the store staging buffers
   if (a.stages > TC_MAX_STAGES) a.stages = TC_MAX_STAGES;
   if (a.stages < 2) return fail("tc_pw_gemm: tile does not fit in shared memory");
   if (int rc = make_map(&a.mapA, p.A, p.K, p.M, p.E, TC_BM)) return rc;
   if (int rc = make_map(&a.mapWh, p.Wh, p.K, p.N, p.E, a.BN)) return rc;
   if (int rc = make_map(&a.mapWl, p.Wl, p.K, p.N, p.E, a.BN)) return rc;
-  const int smem = a.stages * stage_bytes + 1024;
+  if (int rc = make_map(&a.mapC, p.C, p.N, p.M, p.E, TC_BM)) return rc;
+  const int smem = a.stages * stage_bytes + 2 * TC_A_BYTES + 1024;
   static int configured[64] = {0};
   int dev = 0;
   OAT_CUDA(cudaGetDevice(&dev));

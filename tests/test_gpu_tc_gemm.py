@@ -23,6 +23,8 @@ SHAPES = [
     (2, 200, 384, 96, 0, 0),
     (1, 400, 576, 160, 0, 0),
     (2, 130, 160, 960, 1, 0),
+    (1, 200, 64, 224, 0, 0),
+    (1, 100, 32, 8, 0, 0),
     (1, 256, 960, 320, 0, 0),
     (1, 272, 320, 1280, 1, 0),
     (4, 64, 1280, 128, 0, 0),
