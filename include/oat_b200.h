@@ -126,6 +126,26 @@ OAT_API int oat_rip_aggregate(const float* q, int32_t E, int32_t B, int32_t K, i
                       const float* y, int32_t T, float* s, int32_t* kstar,
                       float* sbest, float* plan, void* stream);
 
+/* Gradient-based MAP planner, ONE kernel launch: the Adam-on-latent loops of
+ * `ImitativeModel.forward` (dim/model.py:97-141; algo = -1, one model) and
+ * `RIPAgent.__call__` (rip/agent.py:84-137; algo = OAT_ALGO_*, E models): per step
+ * y = f_0(x; z_0), per-model posteriors mean_b(log_prob - logabsdet) + goal likelihood,
+ * loss aggregation as written, analytic back-propagation to x, torch.optim.Adam update
+ * (lr, betas 0.9/0.999, eps 1e-8), best-x bookkeeping with the post-step x (as written),
+ * finally plan = f_0(x_best).  x [B,T,2] in: initial latent, out: final latent;
+ * x_best/plan [B,T,2] out; z [E,B,64]; goal [B,G,2] or NULL; loss_out [num_steps] or
+ * NULL; workspace: oat_plan_workspace_floats(B, E, T) floats of device scratch.    */
+OAT_API int oat_plan(OatModel* const* models, int32_t num_models, int32_t algo, const float* z,
+             const float* goal, int32_t G, float epsilon, int32_t B, int32_t T,
+             int32_t num_steps, float lr, float* x, float* x_best, float* plan,
+             float* workspace, int64_t workspace_floats, float* loss_out, void* stream);
+OAT_API int64_t oat_plan_workspace_floats(int32_t B, int32_t num_models, int32_t T);
+
+/* `ImitativeModel._goal_likelihood` (dim/model.py:143-171): y_last [B,2] = y[:, -1],
+ * goal [B,G,2] -> rows [B] (per-row log-likelihood, may be NULL) and mean [1].       */
+OAT_API int oat_goal_likelihood(const float* y_last, const float* goal, int32_t B, int32_t G,
+                        float epsilon, float* rows, float* mean, void* stream);
+
 /* `BehaviouralModel.forward` roll-out (cil/model.py:106-127) after the encoder:
  * z [B,64] -> y [B,T,2].                                                          */
 OAT_API int oat_cil_rollout(const OatModel* model, const float* z, int32_t B, int32_t T,

@@ -23,7 +23,7 @@ SYMBOLS = (
     "oat_ensemble_reserve", "oat_transform_visual", "oat_encode", "oat_flow_forward",
     "oat_flow_inverse", "oat_rip_sample_score", "oat_rip_aggregate", "oat_cil_rollout",
     "oat_launch_count", "oat_ensemble_set_pw_impl", "oat_debug_tc_gemm",
-    "oat_set_flow_impl",
+    "oat_set_flow_impl", "oat_plan", "oat_plan_workspace_floats", "oat_goal_likelihood",
 )
 
 
@@ -76,11 +76,17 @@ def lib() -> ctypes.CDLL:
     L.oat_cil_rollout.argtypes = [vp, vp, c_i32, c_i32, vp, vp]
     L.oat_ensemble_set_pw_impl.argtypes = [vp, c_i32]
     L.oat_set_flow_impl.argtypes = [c_i32]
+    L.oat_plan.argtypes = [ctypes.POINTER(vp), c_i32, c_i32, vp, vp, c_i32, c_f, c_i32, c_i32, c_i32,
+                           c_f, vp, vp, vp, vp, c_i64, vp, vp]
+    L.oat_plan_workspace_floats.argtypes = [c_i32, c_i32, c_i32]
+    L.oat_goal_likelihood.argtypes = [vp, vp, c_i32, c_i32, c_f, vp, vp, vp]
     L.oat_debug_tc_gemm.argtypes = [vp, vp, vp, vp, vp, c_i32, c_i32, c_i32, c_i32, c_i32, vp]
     for name in SYMBOLS:
       fn = getattr(L, name, None)
-      if fn is not None and name not in ("oat_last_error", "oat_launch_count"):
+      if fn is not None and name not in ("oat_last_error", "oat_launch_count",
+                                         "oat_plan_workspace_floats"):
         fn.restype = c_int
+    L.oat_plan_workspace_floats.restype = c_i64
     _lib = L
     return L
 

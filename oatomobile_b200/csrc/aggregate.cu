@@ -66,7 +66,52 @@ __global__ void __launch_bounds__(ATHREADS) aggregate_kernel(
   }
 }
 
+// ImitativeModel._goal_likelihood (dim/model.py:143-171): per-row mixture log-likelihood
+// of y[:, -1] under N(goal_g, eps^2 I) with uniform weights, and its batch mean.
+__global__ void __launch_bounds__(256) goal_likelihood_kernel(
+    const float* __restrict__ y_last, const float* __restrict__ goal, int B, int G,
+    float inv_two_eps2, float log_norm, float* __restrict__ rows, float* __restrict__ mean) {
+  __shared__ float part[8];
+  float local = 0.0f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float y0 = y_last[2 * b], y1 = y_last[2 * b + 1];
+    const float* g = goal + (int64_t)b * G * 2;
+    float mx = -INFINITY;
+    for (int i = 0; i < G; ++i) {
+      const float d0 = y0 - g[2 * i], d1 = y1 - g[2 * i + 1];
+      mx = fmaxf(mx, -(d0 * d0 + d1 * d1) * inv_two_eps2);
+    }
+    float se = 0.0f;
+    for (int i = 0; i < G; ++i) {
+      const float d0 = y0 - g[2 * i], d1 = y1 - g[2 * i + 1];
+      se += expf(-(d0 * d0 + d1 * d1) * inv_two_eps2 - mx);
+    }
+    const float ll = mx + logf(se) + log_norm;
+    if (rows) rows[b] = ll;
+    local += ll;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0 && mean) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    *mean = t / (float)B;
+  }
+}
+
 }  // namespace
+
+int launch_goal_likelihood(const float* y_last, const float* goal, int B, int G, float epsilon,
+                           float* rows, float* mean, cudaStream_t stream) {
+  const double eps = epsilon;
+  goal_likelihood_kernel<<<1, 256, 0, stream>>>(
+      y_last, goal, B, G, (float)(1.0 / (2.0 * eps * eps)),
+      (float)(-log(2.0 * 3.14159265358979323846 * eps * eps) - log((double)G)), rows, mean);
+  OAT_LAUNCH_CHECK();
+  return 0;
+}
 
 int launch_aggregate(const float* q, int E, int B, int K, int algo, const float* y, int T,
                      float* s, int32_t* kstar, float* sbest, float* plan,

@@ -231,10 +231,11 @@ int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind
     const HostTensor *wih = P.get(g + "weight_ih", {192, 2}), *whh = P.get(g + "weight_hh", {192, 64}),
                      *bih = P.get(g + "bias_ih", {192}), *bhh = P.get(g + "bias_hh", {192});
     if (!wih || !whh || !bih || !bhh) return fail(P.err);
-    flow.w = P.alloc(kFlowFloats);
+    flow.w = P.alloc(kFlowPlanFloats);
     float* fw = nullptr;
     auto F = [&]() { return P.arena.data() + flow.w; };
     fw = F();
+    for (int i = 0; i < 192 * 64; ++i) fw[kFlowWhhRaw + i] = whh->data[i];
     for (int j = 0; j < 192; ++j) {
       for (int k = 0; k < 64; ++k) fw[kFlowWhh + k * 192 + j] = whh->data[j * 64 + k];
       fw[kFlowWihT + j] = wih->data[j * 2 + 0];
@@ -248,6 +249,7 @@ int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind
                        *w2 = P.get(h + "2.weight", {4, 32}), *b2 = P.get(h + "2.bias", {4});
       if (!w1 || !b1 || !w2 || !b2)
         return fail(P.err + " (the flow head must be MLP(64,[32,4]); sequence.py:61 sizes it by T)");
+      for (int i = 0; i < 32 * 64; ++i) fw[kFlowW1Raw + i] = w1->data[i];
       for (int j = 0; j < 32; ++j) {
         for (int k = 0; k < 64; ++k) fw[kFlowW1T + k * 32 + j] = w1->data[j * 64 + k];
         fw[kFlowB1 + j] = b1->data[j];
@@ -579,6 +581,55 @@ int oat_rip_aggregate(const float* q, int32_t E, int32_t B, int32_t K, int32_t a
   if (!q || !kstar) return fail("oat_rip_aggregate: null argument");
   if (plan && !y) return fail("oat_rip_aggregate: plan requested without y");
   return launch_aggregate(q, E, B, K, algo, y, T, s, kstar, sbest, plan, (cudaStream_t)stream);
+}
+
+int oat_plan(OatModel* const* models, int32_t num_models, int32_t algo, const float* z,
+             const float* goal, int32_t G, float epsilon, int32_t B, int32_t T, int32_t num_steps,
+             float lr, float* x, float* x_best, float* plan, float* workspace,
+             int64_t workspace_floats, float* loss_out, void* stream) {
+  if (B <= 0 || T <= 0) return 0;
+  if (!models || !z || !x || !x_best || !plan || !workspace) return fail("oat_plan: null argument");
+  if (num_models < 1 || num_models > kMaxModels) return fail("oat_plan: bad ensemble size");
+  if (algo < -1 || algo > OAT_ALGO_MA) return fail("oat_plan: unknown algorithm");
+  if (algo == -1 && num_models != 1) return fail("oat_plan: single-model planning takes one model");
+  if (goal && G < 1) return fail("oat_plan: G must be >= 1 when goal is given");
+  if (epsilon <= 0.0f) return fail("oat_plan: epsilon must be positive");
+  if (num_steps < 0) return fail("oat_plan: num_steps must be >= 0");
+  if (workspace_floats < oat_plan_workspace_floats(B, num_models, T))
+    return fail("oat_plan: workspace too small (see oat_plan_workspace_floats)");
+  PlanLaunch p;
+  for (int i = 0; i < kMaxModels; ++i) p.w.p[i] = nullptr;
+  for (int i = 0; i < num_models; ++i) {
+    if (!models[i] || models[i]->kind == OAT_KIND_CIL) return fail("oat_plan: models must be flows");
+    if (int rc = check_device(models[i]->device, "oat_plan")) return rc;
+    p.w.p[i] = models[i]->flow;
+  }
+  p.E = num_models; p.algo = algo; p.z = z; p.goal = goal; p.G = G; p.epsilon = epsilon;
+  p.B = B; p.T = T; p.num_steps = num_steps; p.lr = lr;
+  // workspace: [sync (4 floats)] [post 2*E*B] [adam 4*B*T] [scratch]
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t head = 4 + (size_t)2 * num_models * B + (size_t)4 * B * T;
+  OAT_CUDA(cudaMemsetAsync(workspace, 0, head * sizeof(float), st));
+  p.sync = reinterpret_cast<unsigned int*>(workspace);
+  p.post = workspace + 4;
+  p.adam = p.post + (size_t)2 * num_models * B;
+  p.scratch = p.adam + (size_t)4 * B * T;
+  p.x = x; p.x_best = x_best; p.plan = plan; p.loss_out = loss_out;
+  OAT_CUDA(cudaMemcpyAsync(x_best, x, (size_t)B * T * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return launch_plan(p, st);
+}
+
+int64_t oat_plan_workspace_floats(int32_t B, int32_t num_models, int32_t T) {
+  return (int64_t)(4 + (size_t)2 * num_models * B + (size_t)4 * B * T +
+                   plan_scratch_floats(B, num_models, T));
+}
+
+int oat_goal_likelihood(const float* y_last, const float* goal, int32_t B, int32_t G, float epsilon,
+                        float* rows, float* mean, void* stream) {
+  if (B <= 0) return 0;
+  if (!y_last || !goal || (!rows && !mean)) return fail("oat_goal_likelihood: null argument");
+  if (G < 1 || epsilon <= 0.0f) return fail("oat_goal_likelihood: need G >= 1 and epsilon > 0");
+  return launch_goal_likelihood(y_last, goal, B, G, epsilon, rows, mean, (cudaStream_t)stream);
 }
 
 int oat_cil_rollout(const OatModel* model, const float* z, int32_t B, int32_t T, float* y,

@@ -50,6 +50,11 @@ constexpr int kFlowW2 = kFlowB1 + 32;
 constexpr int kFlowB2 = kFlowW2 + 4 * 32;
 constexpr int kFlowFloats = kFlowB2 + 4;  // 15268 (multiple of 4)
 static_assert(kFlowFloats % 4 == 0, "flow weight image must be float4-copyable");
+// Planner image (planner.cu) = the flow image above followed by the untransposed
+// matrices the backward pass reads: W_hh [192][64], W_1 [32][64].
+constexpr int kFlowWhhRaw = kFlowFloats;
+constexpr int kFlowW1Raw = kFlowWhhRaw + 192 * 64;
+constexpr int kFlowPlanFloats = kFlowW1Raw + 32 * 64;
 // Tensor-core flow image (flow_tc.cu): W_hh / W_1 split into TF32 hi/lo parts and
 // pre-swizzled into the K-major SWIZZLE_128B UMMA layout, + gate/head parameters.
 constexpr int kFlowTcFloats = 29604;
@@ -134,7 +139,30 @@ struct FlowLaunch {
   int skip_model;             // grid.y index that exits immediately (-1: none)
 };
 int launch_flow(const FlowLaunch& a, cudaStream_t stream);
-int launch_flow_tc(const FlowLaunch& a, cudaStream_t stream);  // weights = flow_tc images
+int launch_flow_tc(const FlowLaunch& a, cudaStream_t stream);
+
+struct PlanLaunch {
+  PtrTable w;  // per-model planner images (kFlowPlanFloats)
+  int E, algo;  // algo -1: single model (ImitativeModel.forward)
+  const float* z;
+  const float* goal;
+  int G;
+  float epsilon;
+  int B, T, num_steps;
+  float lr;
+  float* scratch;
+  float* post;
+  unsigned int* sync;
+  float* x;
+  float* x_best;
+  float* plan;
+  float* adam;
+  float* loss_out;
+};
+int launch_plan(const PlanLaunch& p, cudaStream_t stream);
+size_t plan_scratch_floats(int B, int E, int T);
+int launch_goal_likelihood(const float* y_last, const float* goal, int B, int G, float epsilon,
+                           float* rows, float* mean, cudaStream_t stream);  // weights = flow_tc images
 void pack_flow_tc_image(const float* flow_weights, float* image);
 extern int g_flow_impl;  // 1 = tcgen05 (default), 0 = FP32 SIMT
 

@@ -101,14 +101,21 @@ class ImitativeModel(_EncoderModel):
     return ops.goal_likelihood(y, goal, epsilon)[1]
 
   def forward(self, num_steps: int, goal: Optional[torch.Tensor] = None, lr: float = 1e-1,
-              epsilon: float = 1.0, **context: torch.Tensor) -> torch.Tensor:
-    """dim/model.py:76-141 — Adam-on-latent MAP planner, one fused kernel launch."""
+              epsilon: float = 1.0, x0: Optional[torch.Tensor] = None,
+              **context: torch.Tensor) -> torch.Tensor:
+    """dim/model.py:76-141 — Adam-on-latent MAP planner, one fused kernel launch.
+
+    `x0` (extension, [1|B,T,2]) fixes the initial latent; by default it is one random
+    base-distribution sample shared by the whole batch, as at dim/model.py:100-105."""
     if "visual_features" not in context:
       raise ValueError("Missing `visual_features` keyword argument.")
     batch_size = context["visual_features"].shape[0]
     z = self._params(**context)
-    # dim/model.py:100-105: one random base sample shared by the whole batch.
-    x0 = torch.randn(1, *self._output_shape, device=z.device).repeat(batch_size, 1, 1)
+    if x0 is None:
+      x0 = torch.randn(1, *self._output_shape, device=z.device)
+    x0 = x0.to(z.device, torch.float32).reshape(-1, *self._output_shape)
+    if x0.shape[0] == 1:
+      x0 = x0.repeat(batch_size, 1, 1)
     return ops.plan([self.native_handle()], z.unsqueeze(0), x0, num_steps=num_steps, lr=lr,
                     goal=goal, epsilon=epsilon, algorithm=None)[0]
 

@@ -132,3 +132,50 @@ def cil_rollout(model: N.ModelHandle, z: torch.Tensor, T: int) -> torch.Tensor:
     N.check(N.lib().oat_cil_rollout(model.ptr, z.data_ptr(), B, T, y.data_ptr(),
                                     N.stream_ptr(z.device)))
   return y
+
+
+def goal_likelihood(y: torch.Tensor, goal: torch.Tensor, epsilon: float = 1.0):
+  """dim/model.py:143-171 — y [B,T,2], goal [B,G,2] -> (per-row [B], batch mean [])."""
+  y = N.require_cuda_f32(y, "y")
+  goal = N.require_cuda_f32(goal, "goal")
+  B, G = goal.shape[0], goal.shape[1]
+  y_last = y[:, -1, :].contiguous()
+  rows = torch.empty(B, device=y.device, dtype=torch.float32)
+  mean = torch.empty((), device=y.device, dtype=torch.float32)
+  with torch.cuda.device(y.device):
+    N.check(N.lib().oat_goal_likelihood(y_last.data_ptr(), goal.data_ptr(), B, G, float(epsilon),
+                                        rows.data_ptr(), mean.data_ptr(), N.stream_ptr(y.device)))
+  return rows, mean
+
+
+def plan(models, z: torch.Tensor, x0: torch.Tensor, num_steps: int, lr: float,
+         goal: Optional[torch.Tensor], epsilon: float, algorithm: Optional[str],
+         want_loss: bool = False):
+  """The gradient-based MAP planner of dim/model.py:97-141 (algorithm=None, one model)
+  and rip/agent.py:84-137 (algorithm in WCM|BCM|MA), one fused kernel launch.
+
+  models: list of `_native.ModelHandle`; z [E,B,64]; x0 [B,T,2] initial latent.
+  Returns (plan [B,T,2], x_best [B,T,2], losses [num_steps] | None)."""
+  import ctypes
+  z = N.require_cuda_f32(z, "z")
+  x = N.require_cuda_f32(x0, "x0").clone()
+  E, B, _ = z.shape
+  T = x.shape[1]
+  if E != len(models):
+    raise ValueError("z has %d models, got %d handles" % (E, len(models)))
+  algo = -1 if algorithm is None else N.ALGORITHMS[algorithm]
+  if goal is not None:
+    goal = N.require_cuda_f32(goal, "goal")
+  G = 0 if goal is None else goal.shape[1]
+  x_best = torch.empty_like(x)
+  out = torch.empty_like(x)
+  nws = int(N.lib().oat_plan_workspace_floats(B, E, T))
+  ws = torch.empty(nws, device=x.device, dtype=torch.float32)
+  losses = torch.empty(max(num_steps, 1), device=x.device, dtype=torch.float32) if want_loss else None
+  arr = (ctypes.c_void_p * E)(*[m.ptr.value for m in models])
+  with torch.cuda.device(x.device):
+    N.check(N.lib().oat_plan(arr, E, algo, z.data_ptr(), N.ptr(goal), G, float(epsilon), B, T,
+                             int(num_steps), float(lr), x.data_ptr(), x_best.data_ptr(),
+                             out.data_ptr(), ws.data_ptr(), nws, N.ptr(losses),
+                             N.stream_ptr(x.device)))
+  return out, x_best, losses

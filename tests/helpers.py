@@ -47,3 +47,17 @@ def top2_gap(s):
   s = torch.as_tensor(s, dtype=torch.float64)
   v, _ = torch.sort(s, dim=1)
   return ((v[:, 1] - v[:, 0]) / torch.clamp(v[:, 0].abs(), min=1.0))
+
+
+def observation(inp, b):
+  """A raw simulator observation for scene b (HWC lidar, xyz goals) — same as
+  tests/golden/make_golden.py::observation."""
+  goal3 = np.concatenate([inp["goal"][b].numpy(), np.zeros((inp["goal"].shape[1], 1))], -1)
+  return {
+      "bird_view_camera_cityscapes": np.zeros((4, 4, 3), np.float32),
+      "lidar": np.ascontiguousarray(inp["lidar"][b].permute(1, 2, 0).numpy()),
+      "velocity": inp["velocity"][b].numpy(),
+      "is_at_traffic_light": int(inp["is_at_traffic_light"][b, 0]),
+      "traffic_light_state": int(inp["traffic_light_state"][b, 0]),
+      "goal": goal3.astype(np.float32),
+  }
