@@ -285,19 +285,24 @@ def run_gpu_arm(args):
             "aggregate": stage_ms("aggregate_begin", "aggregate_end")}
 
   # ---- e2e: host (pinned) buffers through the public pipeline --------------------
-  pipe = HostRIPPipeline(scorer, dev)
-  for _ in range(3):
-    pipe(host)
+  pipe = HostRIPPipeline(scorer, dev, chunks=args.e2e_chunks)
+  for _ in pipe.stream(host for _ in range(3)):
+    pass
   barrier()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
   t_host0 = time.perf_counter()
-  for _ in range(args.steps):
-    res = pipe(host)
+  checksum = 0.0
+  for res in pipe.stream(host for _ in range(args.steps)):
+    checksum += float(res["plan"][0, 0, 0])  # the host really reads every step's result
   e1.record()
   barrier()
   e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_host0))
-  checksum = float(res["plan"].sum())
+  # latency form: one blocking call per step (no cross-step overlap)
+  l0 = time.perf_counter()
+  for _ in range(max(args.steps // 4, 3)):
+    res = pipe(host)
+  e2e_blocking_ms = 1e3 * (time.perf_counter() - l0) / max(args.steps // 4, 3)
 
   # ---- max over ranks ------------------------------------------------------------
   t = torch.tensor([elapsed_ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -318,15 +323,23 @@ def run_gpu_arm(args):
     sm_mhz = clocks.get("sm_mhz") or 0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12 if sm_mhz else None
     tensor_peak = peaks["bf16_tflops_sustained"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):  # dram bytes/launch from the last `ncu --set full` capture
+      traffic = json.load(open(tpath)).get("flow_tc_kernel_pair_bytes")
     roofline = {
-        "kernel": "oat::flow_kernel<0|1> (sample + score launches)",
+        "kernel": "oat::flow_tc_kernel<0> + <1> (sample + score launches of one step)",
         "bound": "tensor", "achieved": flow_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
-        "frac": flow_tflops / tensor_peak, "traffic": None,
+        "frac": flow_tflops / tensor_peak, "traffic": traffic,
         "peak_source": peaks["source"] + ", bf16 dense sustained",
-        "pipe": "fp32-simt (round 1: the recurrent GEMM is FP32 FFMA, not yet tcgen05)",
+        "pipe": "tcgen05.mma kind::tf32, 3xTF32 error compensation (3 TF32 MMAs per algorithmic "
+                "MMA, TF32 = 1/2 bf16 rate -> ceiling of this formulation = peak/6), co-limited "
+                "by the FP32/MUFU gate math of the GRU",
+        "frac_of_3xtf32_ceiling": flow_tflops / (tensor_peak / 6.0),
         "fp32_simt_peak": fp32_peak,
-        "frac_fp32_simt": (flow_tflops / fp32_peak) if fp32_peak else None,
+        "x_fp32_simt_peak": (flow_tflops / fp32_peak) if fp32_peak else None,
         "algorithmic_flop_per_launch_pair": flow_flop,
+        "algorithmic_bytes_per_launch_pair": rows * (T_STEPS * 16 + 4 * passes),
         "ms_per_launch_pair": stages["flow"],
         "encoder": {"ms": stages["encode"],
                     "tflops": e_local * scenes * ENC_MFLOP_PER_IMAGE * 1e6 /
@@ -354,7 +367,11 @@ def run_gpu_arm(args):
         "stages_ms": stages, "clocks": clocks, "gpu_launches": int(launches) * world,
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(pipe.h2d_bytes) * world,
-                "d2h_bytes_per_step": int(pipe.d2h_bytes) * world, "checksum": checksum},
+                "d2h_bytes_per_step": int(pipe.d2h_bytes) * world, "checksum": checksum,
+                "pipeline": "streamed: pinned H2D of step i+1 (copy stream, double-buffered device "
+                            "inputs) overlaps the kernels of step i; every step's plans are read "
+                            "back and touched on the host",
+                "blocking_call_ms": e2e_blocking_ms},
         "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -378,6 +395,8 @@ def main():
   ap.add_argument("--cpu-scenes", type=int, default=16,
                   help="scenes per CPU-baseline step (bounded sample of the workload)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--e2e-chunks", type=int, default=1,
+                  help="slices of the batch pipelined H2D-vs-compute in the e2e arm")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference_arm(args)

@@ -88,6 +88,11 @@ OAT_API int oat_set_flow_impl(int32_t impl);
 OAT_API int oat_transform_visual(const float* lidar, int32_t B, int32_t C, int32_t H, int32_t W,
                          float* visual, void* stream);
 
+/* Same, reading the simulator / on-disk layout lidar [B,H,W,C] directly, i.e. fused with
+ * the HWC->CHW transposes of rip/agent.py:69 and datasets/carla.py:138-140.           */
+OAT_API int oat_transform_visual_hwc(const float* lidar, int32_t B, int32_t H, int32_t W, int32_t C,
+                             float* visual, void* stream);
+
 /* `ImitativeModel._params` (dim/model.py:173-219) for every model of the ensemble:
  * visual [B,C,100,100] (shared), scalars [B,S] = cat(velocity(3), is_at_traffic_light(1),
  * traffic_light_state(1) [, mode(1) for CIL]) -> z [E,B,64].                      */
@@ -145,6 +150,13 @@ OAT_API int64_t oat_plan_workspace_floats(int32_t B, int32_t num_models, int32_t
  * goal [B,G,2] -> rows [B] (per-row log-likelihood, may be NULL) and mean [1].       */
 OAT_API int oat_goal_likelihood(const float* y_last, const float* goal, int32_t B, int32_t G,
                         float epsilon, float* rows, float* mean, void* stream);
+
+/* `carla_lidar_measurement_to_ndarray` (oatomobile/utils/carla.py:165-233): point cloud
+ * points [N,3] -> BEV histogram bev [200,200,2] float32 in {0,.2,..,1} (x, y, below|above
+ * z = -2.5), bit-exact with the NumPy reference.  counts: 80000 uint32 of scratch.      */
+OAT_API int oat_lidar_bev(const float* points, int64_t num_points, int32_t pixels_per_meter,
+                  int32_t hist_max_per_pixel, int32_t meters_max, uint32_t* counts, float* bev,
+                  void* stream);
 
 /* `BehaviouralModel.forward` roll-out (cil/model.py:106-127) after the encoder:
  * z [B,64] -> y [B,T,2].                                                          */

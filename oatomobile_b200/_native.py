@@ -24,6 +24,7 @@ SYMBOLS = (
     "oat_flow_inverse", "oat_rip_sample_score", "oat_rip_aggregate", "oat_cil_rollout",
     "oat_launch_count", "oat_ensemble_set_pw_impl", "oat_debug_tc_gemm",
     "oat_set_flow_impl", "oat_plan", "oat_plan_workspace_floats", "oat_goal_likelihood",
+    "oat_transform_visual_hwc", "oat_lidar_bev",
 )
 
 
@@ -67,6 +68,7 @@ def lib() -> ctypes.CDLL:
     L.oat_ensemble_reserve.argtypes = [vp, c_i32]
     L.oat_transform_visual.argtypes = [vp, c_i32, c_i32, c_i32, c_i32, vp, vp]
     L.oat_encode.argtypes = [vp, vp, vp, c_i32, vp, vp]
+    L.oat_transform_visual_hwc.argtypes = [vp, c_i32, c_i32, c_i32, c_i32, vp, vp]
     L.oat_flow_forward.argtypes = [vp, vp, vp, c_i64, c_i32, c_i32, vp, vp, vp]
     L.oat_flow_inverse.argtypes = [vp, vp, vp, c_i64, c_i32, c_i32, vp, vp, vp, vp]
     L.oat_rip_sample_score.argtypes = [vp, c_i32, vp, vp, vp, c_i32, c_f, c_i32, c_i32, c_i32,
@@ -79,6 +81,7 @@ def lib() -> ctypes.CDLL:
     L.oat_plan.argtypes = [ctypes.POINTER(vp), c_i32, c_i32, vp, vp, c_i32, c_f, c_i32, c_i32, c_i32,
                            c_f, vp, vp, vp, vp, c_i64, vp, vp]
     L.oat_plan_workspace_floats.argtypes = [c_i32, c_i32, c_i32]
+    L.oat_lidar_bev.argtypes = [vp, c_i64, c_i32, c_i32, c_i32, vp, vp, vp]
     L.oat_goal_likelihood.argtypes = [vp, vp, c_i32, c_i32, c_f, vp, vp, vp]
     L.oat_debug_tc_gemm.argtypes = [vp, vp, vp, vp, vp, c_i32, c_i32, c_i32, c_i32, c_i32, vp]
     for name in SYMBOLS:

@@ -483,6 +483,14 @@ int oat_transform_visual(const float* lidar, int32_t B, int32_t C, int32_t H, in
   return launch_transform_visual(lidar, B, C, H, W, visual, (cudaStream_t)stream);
 }
 
+int oat_transform_visual_hwc(const float* lidar, int32_t B, int32_t H, int32_t W, int32_t C,
+                             float* visual, void* stream) {
+  if (B <= 0 || C <= 0) return 0;
+  if (!lidar || !visual) return fail("oat_transform_visual_hwc: null pointer");
+  if (H < 2 || W < 2) return fail("oat_transform_visual_hwc: input must be at least 2x2");
+  return launch_transform_visual(lidar, B, C, H, W, visual, (cudaStream_t)stream, true);
+}
+
 int oat_encode(OatEnsemble* ens, const float* visual, const float* scalars, int32_t B, float* z,
                void* stream) {
   if (B <= 0) return 0;
@@ -622,6 +630,15 @@ int oat_plan(OatModel* const* models, int32_t num_models, int32_t algo, const fl
 int64_t oat_plan_workspace_floats(int32_t B, int32_t num_models, int32_t T) {
   return (int64_t)(4 + (size_t)2 * num_models * B + (size_t)4 * B * T +
                    plan_scratch_floats(B, num_models, T));
+}
+
+int oat_lidar_bev(const float* points, int64_t num_points, int32_t pixels_per_meter,
+                  int32_t hist_max_per_pixel, int32_t meters_max, uint32_t* counts, float* bev,
+                  void* stream) {
+  if (!counts || !bev || (num_points > 0 && !points)) return fail("oat_lidar_bev: null argument");
+  if (num_points < 0) return fail("oat_lidar_bev: negative point count");
+  return launch_lidar_bev(points, num_points, pixels_per_meter, hist_max_per_pixel, meters_max, counts,
+                          bev, (cudaStream_t)stream);
 }
 
 int oat_goal_likelihood(const float* y_last, const float* goal, int32_t B, int32_t G, float epsilon,

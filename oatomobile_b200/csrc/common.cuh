@@ -161,6 +161,8 @@ struct PlanLaunch {
 };
 int launch_plan(const PlanLaunch& p, cudaStream_t stream);
 size_t plan_scratch_floats(int B, int E, int T);
+int launch_lidar_bev(const float* points, int64_t n, int pixels_per_meter, int hist_max,
+                     int meters_max, unsigned int* counts, float* out, cudaStream_t stream);
 int launch_goal_likelihood(const float* y_last, const float* goal, int B, int G, float epsilon,
                            float* rows, float* mean, cudaStream_t stream);  // weights = flow_tc images
 void pack_flow_tc_image(const float* flow_weights, float* image);
@@ -171,7 +173,7 @@ int launch_aggregate(const float* q, int E, int B, int K, int algo, const float*
                      cudaStream_t stream);
 
 int launch_transform_visual(const float* lidar, int B, int C, int H, int W, float* visual,
-                            cudaStream_t stream);
+                            cudaStream_t stream, bool hwc = false);
 
 int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars, int B,
                     float* z, cudaStream_t stream);

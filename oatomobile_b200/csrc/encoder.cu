@@ -21,8 +21,9 @@ __device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.0f), 
 // a1. bilinear 2x-ish resize (align_corners=True) fused with the H<->W swap.
 // out[b,c,i,j] = R[b,c,j,i],  R[p,q] = bilinear(src, p*(H-1)/(OH-1), q*(W-1)/(OW-1)).
 // ---------------------------------------------------------------------------
+template <bool HWC>
 __global__ void __launch_bounds__(256) transform_visual_kernel(
-    const float* __restrict__ lidar, int BC, int H, int W, float* __restrict__ out,
+    const float* __restrict__ lidar, int BC, int C, int H, int W, float* __restrict__ out,
     float scale_h, float scale_w) {
   constexpr int O = 100;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,9 +37,13 @@ __global__ void __launch_bounds__(256) transform_visual_kernel(
   const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
   const float ly = sy - (float)y0, lx = sx - (float)x0;
   const float hy = 1.0f - ly, hx = 1.0f - lx;
-  const float* src = lidar + bc * H * W;
-  const float v00 = __ldg(src + y0 * W + x0), v01 = __ldg(src + y0 * W + x1);
-  const float v10 = __ldg(src + y1 * W + x0), v11 = __ldg(src + y1 * W + x1);
+  // NCHW: plane (b,c) is contiguous; HWC (the on-disk / simulator layout): channel-strided
+  const int64_t b = bc / C;
+  const int c = (int)(bc % C);
+  const float* src = HWC ? lidar + b * H * W * C + c : lidar + bc * H * W;
+  const int es = HWC ? C : 1;
+  const float v00 = __ldg(src + (int64_t)(y0 * W + x0) * es), v01 = __ldg(src + (int64_t)(y0 * W + x1) * es);
+  const float v10 = __ldg(src + (int64_t)(y1 * W + x0) * es), v11 = __ldg(src + (int64_t)(y1 * W + x1) * es);
   // same association as ATen: hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11)
   out[idx] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
 }
@@ -372,13 +377,17 @@ __global__ void __launch_bounds__(64) merger_kernel(const __grid_constant__ Merg
 }  // namespace
 
 int launch_transform_visual(const float* lidar, int B, int C, int H, int W, float* visual,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, bool hwc) {
   if (B <= 0) return 0;
   const int64_t total = (int64_t)B * C * 100 * 100;
   // ATen: scale = (in-1)/(out-1) evaluated in float for align_corners=True
   const float sh = (float)(H - 1) / 99.0f, sw = (float)(W - 1) / 99.0f;
-  transform_visual_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-      lidar, B * C, H, W, visual, sh, sw);
+  if (hwc)
+    transform_visual_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        lidar, B * C, C, H, W, visual, sh, sw);
+  else
+    transform_visual_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        lidar, B * C, C, H, W, visual, sh, sw);
   OAT_LAUNCH_CHECK();
   return 0;
 }

@@ -14,8 +14,8 @@
 // Truncation of the tensor core's accumulate is kept at 8 MMAs per accumulator by
 // issuing the 16 small correction MMAs (h_lo.W_hi, h_hi.W_lo) before the 8 main ones.
 //
-// Roles: warps 0-7 compute (warp w: TMEM lanes 32*(w%4).., hidden units 32*(w/4)..),
-// warp 8 = TMEM allocator + single-thread MMA issuer.  The recurrent MMA of step t+1
+// Roles: warps 0-15 compute (warp w: TMEM lanes 32*(w%4).., hidden units 16*(w/4)..),
+// warp 16 = TMEM allocator + single-thread MMA issuer.  The recurrent MMA of step t+1
 // is issued right after h_t is published, so it overlaps the head/flow update of t.
 #include <cstring>
 
@@ -25,7 +25,8 @@ namespace oat {
 namespace {
 
 constexpr int TR = 128;                 // rows per CTA
-constexpr int TTHREADS = 288;           // 8 compute warps + 1 MMA warp
+constexpr int TTHREADS = 544;           // 16 compute warps + 1 MMA warp
+constexpr int TCOMPUTE = 512;
 constexpr int kH_BYTES = TR * 128;      // one k-block (32 fp32) of the state tile: 16 KB
 constexpr int kW_BYTES = 192 * 128;     // one k-block of W_hh: 24 KB
 constexpr int kW1_BYTES = 32 * 128;     // one k-block of W_1: 4 KB
@@ -156,17 +157,17 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
   const int T = a.T, T2 = 2 * a.T;
   const int64_t row0 = (int64_t)blockIdx.x * TR;
   const int rows_here = (int)min((int64_t)TR, a.N - row0);
-  const uint32_t bar_h = smem_u32(&bars[0]);   // h_t published (256 arrivals)
+  const uint32_t bar_h = smem_u32(&bars[0]);   // h_t published (512 arrivals)
   const uint32_t bar_d = smem_u32(&bars[1]);   // recurrent accumulator ready (commit)
   const uint32_t bar_d2 = smem_u32(&bars[2]);  // head accumulator ready (commit)
 
   if (tid == 0) {
-    mbar_init(bar_h, 256);
+    mbar_init(bar_h, TCOMPUTE);
     mbar_init(bar_d, 1);
     mbar_init(bar_d2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_slot)),
                  "r"(256)
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // weight image -> async proxy
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
     }
   } else {
     // ===================== compute warps =====================
-    const int q = warp & 3, hf = warp >> 2;
+    const int q = warp & 3, ug = warp >> 2;        // lane quadrant, unit group (16 units)
     const int row = q * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const float* gate = reinterpret_cast<const float*>(sptr + OFF_GATE);
@@ -256,13 +257,16 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
     const float* B2 = reinterpret_cast<const float*>(sptr + OFF_B2);
     float* yprev = reinterpret_cast<float*>(sptr + OFF_YPREV);
     float* io = reinterpret_cast<float*>(sptr + OFF_IO);
-    const uint32_t hhi_row = sbase + OFF_HHI + hf * kH_BYTES + row * 128;
-    const uint32_t hlo_row = sbase + OFF_HLO + hf * kH_BYTES + row * 128;
+    // units 16*ug .. +15 live in k-block ug/2, 16-byte chunks (ug%2)*4 .. +3 of the row
+    const uint32_t hhi_row = sbase + OFF_HHI + (ug >> 1) * kH_BYTES + row * 128;
+    const uint32_t hlo_row = sbase + OFF_HLO + (ug >> 1) * kH_BYTES + row * 128;
+    const int hf = ug;  // "half 0" below = the four warps with ug == 0 (they own one row each)
 
-    auto publish_h = [&](const float (&h)[32]) {
+    auto publish_h = [&](const float (&h)[16]) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t off = (uint32_t)((c ^ (row & 7)) << 4);  // SWIZZLE_128B: chunk ^= row % 8
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t chunk = (uint32_t)((ug & 1) * 4 + c);
+        const uint32_t off = (chunk ^ (uint32_t)(row & 7)) << 4;  // SWIZZLE_128B: chunk ^= row % 8
         const uint32_t h0 = tf32_hi(h[4 * c]), h1 = tf32_hi(h[4 * c + 1]),
                        h2 = tf32_hi(h[4 * c + 2]), h3 = tf32_hi(h[4 * c + 3]);
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(hhi_row + off), "r"(h0),
@@ -278,52 +282,55 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
       mbar_arrive(bar_h);
     };
 
-    // h_0 = z[row / rows_per_z], this thread's 32 hidden units
-    float h[32];
+    // h_0 = z[row / rows_per_z], this thread's 16 hidden units
+    float h[16];
     {
       const float* zb = a.z + (int64_t)model * a.z_model_stride;
       if (row < rows_here) {
-        const float4* zr = reinterpret_cast<const float4*>(zb + ((row0 + row) / a.rows_per_z) * kHidden + hf * 32);
+        const float4* zr = reinterpret_cast<const float4*>(zb + ((row0 + row) / a.rows_per_z) * kHidden + ug * 16);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           const float4 v = __ldg(zr + c);
           h[4 * c] = v.x; h[4 * c + 1] = v.y; h[4 * c + 2] = v.z; h[4 * c + 3] = v.w;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) h[i] = 0.0f;
+        for (int i = 0; i < 16; ++i) h[i] = 0.0f;
       }
     }
     publish_h(h);
 
     float sumsq = 0.0f, sumlog = 0.0f, goal_ll = 0.0f;
     for (int t = 0; t < T; ++t) {
-      // ---- gates: r|z|n pre-activations from TMEM columns [g*64 + hf*32, +32) -----------
+      // ---- gates: r|z|n pre-activations from TMEM columns [g*64 + ug*16, +16) ------------
       mbar_wait(bar_d, (uint32_t)(t & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const float2 yp = *reinterpret_cast<const float2*>(yprev + 2 * row);
-#pragma unroll
-      for (int half16 = 0; half16 < 2; ++half16) {
+      {
         uint32_t ar[16], az[16], an[16];
-        const uint32_t col = (uint32_t)(hf * 32 + half16 * 16);
+        const uint32_t col = (uint32_t)(ug * 16);
         tmem_ld16_nowait(trow + col, ar);
         tmem_ld16_nowait(trow + 64 + col, az);
         tmem_ld16_nowait(trow + 128 + col, an);
         tmem_wait_ld();
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const int j = hf * 32 + half16 * 16 + u;
+          const int j = ug * 16 + u;
           const float4 g0 = *reinterpret_cast<const float4*>(gate + j * 12);      // wr0 wr1 br wz0
           const float4 g1 = *reinterpret_cast<const float4*>(gate + j * 12 + 4);  // wz1 bz wn0 wn1
           const float2 g2 = *reinterpret_cast<const float2*>(gate + j * 12 + 8);  // bin bhn
           const float ir = fmaf(g0.y, yp.y, fmaf(g0.x, yp.x, g0.z));
           const float iz = fmaf(g1.x, yp.y, fmaf(g0.w, yp.x, g1.y));
           const float in_ = fmaf(g1.w, yp.y, fmaf(g1.z, yp.x, g2.x));
-          const float rr = sigmoid_fast(ir + __uint_as_float(ar[u]));
-          const float gg = sigmoid_fast(iz + __uint_as_float(az[u]));
+          // r = 1/(1+e^-a), g = 1/(1+e^-b) with ONE reciprocal: 1/(A*B) * B, 1/(A*B) * A
+          // (exponent clamped at 40 so ea*eb stays finite; sigmoid(-40) = 4e-18 either way)
+          const float ea = 1.0f + __expf(fminf(-(ir + __uint_as_float(ar[u])), 40.0f));
+          const float eb = 1.0f + __expf(fminf(-(iz + __uint_as_float(az[u])), 40.0f));
+          const float inv = __fdividef(1.0f, ea * eb);
+          const float rr = inv * eb;
+          const float gg = inv * ea;
           const float nn = tanh_fast(fmaf(rr, __uint_as_float(an[u]) + g2.y, in_));
-          const int hi = half16 * 16 + u;
-          h[hi] = fmaf(gg, h[hi] - nn, nn);
+          h[u] = fmaf(gg, h[u] - nn, nn);
         }
       }
       publish_h(h);  // -> head MMA of step t and recurrent MMA of step t+1
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // y_t visible to all 8 compute warps
+      asm volatile("bar.sync 1, 512;" ::: "memory");  // y_t visible to all 16 compute warps
     }
 
     if (hf == 0 && row < rows_here) {
@@ -411,7 +418,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
       for (int i = tid; i < n; i += TTHREADS) dst[i] = io[i];
     }
   }
-  if (warp == 8) {
+  if (warp == 16) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256)
                  : "memory");

@@ -17,17 +17,18 @@
 // round-robin over `C` accumulators by k-block (C = ceil(K/200)); the epilogue adds
 // the C+1 partial tiles in round-to-nearest fp32.  Error -> (K/8)*6e-8/C <= 1.5e-6.
 //
-// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
-//   warp 8   TMA producer: A tile [128 x 32] fp32 + W_hi/W_lo tiles [BN x 32] per
+// Structure (one persistent CTA per SM, 448 threads, warp-specialised):
+//   warp 12  TMA producer: A tile [128 x 32] fp32 + W_hi/W_lo tiles [BN x 32] per
 //            k-block, 128B-swizzled, completion on an mbarrier (expect_tx);
-//   warps4-7 splitters: turn the raw A tile into a_hi (in place) and a_lo (second
+//   warps8-11 splitters: turn the raw A tile into a_hi (in place) and a_lo (second
 //            buffer) in shared memory — the split is element-wise, so it is
 //            layout-agnostic w.r.t. the TMA swizzle; fence.proxy.async hands the
 //            tiles to the tensor core;
-//   warp 9   MMA issuer: one elected thread issues 3 tcgen05.mma.kind::tf32 per
+//   warp 13  MMA issuer: one elected thread issues 3 tcgen05.mma.kind::tf32 per
 //            8-wide k-slice into a TMEM accumulator (128 lanes x BN columns fp32),
 //            tcgen05.commit releases smem stages / publishes the accumulator;
-//   warps0-3 epilogue: tcgen05.ld 32x32b (one output row per thread), RN sum of the
+//   warps0-7 epilogue (two groups of 4, alternating 32-column slabs): tcgen05.ld 32x32b
+//            (one output row per thread), RN sum of the
 //            partial accumulators, folded-BN bias, ReLU6, residual; 32-column slabs
 //            are staged in 128B-swizzled shared memory and written with TMA stores
 //            (cp.async.bulk.tensor, double-buffered), which also clip the M/N tails.
@@ -46,7 +47,7 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // 32 fp32 = 128 B = one swizzle atom row
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;  // 8 epilogue + 4 splitter warps + TMA + MMA
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_TMEM_COLS = 512;
@@ -184,18 +185,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), 128);
+      mbar_init(bar_tempty(i), 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {  // TMEM allocation is a warp-wide operation
+  if (warp == 13) {  // TMEM allocation is a warp-wide operation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_slot)),
                  "r"(TC_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == 12 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapWh)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapWl)) : "memory");
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
   const int tiles_per_model = a.m_tiles * a.n_tiles;
   const int num_tiles = tiles_per_model * a.E;
 
-  if (warp == 8) {
+  if (warp == 12) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = BN
@@ -264,9 +265,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
         umma_commit(bar_tfull(ab));   // accumulators complete
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 8) {
     // ===================== splitters (128 threads) =====================
-    const int st = threadIdx.x - 128;
+    const int st = threadIdx.x - 256;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int kb = 0; kb < k_blocks; ++kb, ++it) {
@@ -299,11 +300,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
       }
     }
   } else {
-    // ===================== epilogue (warps 0-3: TMEM lanes 32*warp..) =====================
-    uint32_t lt = 0, slab_it = 0;
+    // ===== epilogue (warps 0-7: group = warp/4 takes slabs of its parity, TMEM lanes 32*(warp%4)..) =====
+    uint32_t lt = 0;
     const int C = a.chunks;
     const int used = k_blocks < C ? k_blocks : C;  // main accumulators actually written
-    const int et = threadIdx.x;                    // 0..127
+    const int grp = warp >> 2, qd = warp & 3;      // slab parity, TMEM lane quadrant
+    const int et = threadIdx.x & 127;              // thread index inside the group
+    const uint32_t sbuf = stage_out + (uint32_t)grp * (uint32_t)TC_A_BYTES;  // one staging tile per group
+    const int bar_id = 2 + grp;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
       const int e = t / tiles_per_model, r = t % tiles_per_model;
       const int m0 = (r / a.n_tiles) * TC_BM, n0 = (r % a.n_tiles) * BN;
@@ -311,17 +315,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
       const uint32_t aph = (a.nbuf == 2) ? ((lt >> 1) & 1) : (lt & 1);
       mbar_wait(bar_tfull(ab), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int rrow_i = warp * 32 + lane;         // row inside the tile = TMEM lane
+      const int rrow_i = qd * 32 + lane;           // row inside the tile = TMEM lane
       const int row = m0 + rrow_i;
       const bool row_ok = row < a.M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * (C + 1) * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * (C + 1) * BN);
       const float* __restrict__ bias = a.bias + (int64_t)e * a.N;
       const float* __restrict__ rrow = (a.R && row_ok) ? a.R + ((int64_t)e * a.M + row) * a.N : nullptr;
-      for (int c0 = 0; c0 < BN; c0 += 32, ++slab_it) {
-        const uint32_t sbuf = stage_out + (slab_it & 1) * (uint32_t)TC_A_BYTES;
-        // the TMA store that last read this staging buffer (2 slabs ago) must have drained
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+      for (int c0 = grp * 32; c0 < BN; c0 += 64) {
+        // the TMA store that last read this group's staging tile must have drained
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {
           const int c = c0 + hc * 16;
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (et == 0 && n0 + c0 < a.N) tma_store_3d(&a.mapC, sbuf, n0 + c0, m0, e);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 13) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(TC_TMEM_COLS)

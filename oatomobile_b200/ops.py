@@ -21,6 +21,17 @@ def transform_visual(lidar: torch.Tensor) -> torch.Tensor:
   return out
 
 
+def transform_visual_hwc(lidar: torch.Tensor) -> torch.Tensor:
+  """[B,H,W,C] (simulator / on-disk layout) -> [B,C,100,100]: HWC->CHW, resize, H<->W fused."""
+  lidar = N.require_cuda_f32(lidar, "lidar")
+  B, H, W, C = lidar.shape
+  out = torch.empty(B, C, 100, 100, device=lidar.device, dtype=torch.float32)
+  with torch.cuda.device(lidar.device):
+    N.check(N.lib().oat_transform_visual_hwc(lidar.data_ptr(), B, H, W, C, out.data_ptr(),
+                                             N.stream_ptr(lidar.device)))
+  return out
+
+
 def encode(ens: N.EnsembleHandle, visual: torch.Tensor, scalars: torch.Tensor) -> torch.Tensor:
   """dim/model.py:173-219 for all E models: -> z [E,B,64]."""
   visual = N.require_cuda_f32(visual, "visual_features")
@@ -179,3 +190,17 @@ def plan(models, z: torch.Tensor, x0: torch.Tensor, num_steps: int, lr: float,
                              out.data_ptr(), ws.data_ptr(), nws, N.ptr(losses),
                              N.stream_ptr(x.device)))
   return out, x_best, losses
+
+
+def lidar_bev(points: torch.Tensor, pixels_per_meter: int = 2, hist_max_per_pixel: int = 5,
+              meters_max: int = 50) -> torch.Tensor:
+  """oatomobile/utils/carla.py:165-233 — points [N,3] -> BEV histogram [200,200,2]."""
+  points = N.require_cuda_f32(points, "points")
+  n = points.shape[0]
+  counts = torch.empty(200 * 200 * 2, device=points.device, dtype=torch.int32)
+  out = torch.empty(200, 200, 2, device=points.device, dtype=torch.float32)
+  with torch.cuda.device(points.device):
+    N.check(N.lib().oat_lidar_bev(points.data_ptr() if n else None, n, pixels_per_meter,
+                                  hist_max_per_pixel, meters_max, counts.data_ptr(),
+                                  out.data_ptr(), N.stream_ptr(points.device)))
+  return out

@@ -72,11 +72,20 @@ def install():
   _stub("imageio")
   plt = _stub("matplotlib.pyplot")
   _stub("matplotlib", use=lambda *a, **k: None, pyplot=plt)
-  for extra in ("tree", "wget", "pygame", "transforms3d", "skimage", "seaborn"):
+  class _AnyModule(types.ModuleType):  # attribute access yields dummy classes (type hints)
+
+    def __getattr__(self, name):
+      if name.startswith("__"):
+        raise AttributeError(name)
+      return type(name, (), {})
+
+  for extra in ("tree", "wget", "pygame", "transforms3d", "transforms3d.euler", "skimage",
+                "skimage.transform", "seaborn", "carla"):
     try:
       __import__(extra)
     except Exception:  # absent: harmless stub, never touched on the hot path
-      _stub(extra)
+      if extra not in sys.modules:
+        sys.modules[extra] = _AnyModule(extra)
 
   if REFERENCE_ROOT not in sys.path:
     sys.path.insert(0, REFERENCE_ROOT)

@@ -411,3 +411,20 @@ def interpolate_plan(plan):
   tq = np.arange(0, int(t_idx[-1])).astype(np.float64)
   xy = np.stack([np.interp(tq, t_idx, plan[:, d].astype(np.float64)) for d in range(2)], -1)
   return np.c_[xy, np.zeros((xy.shape[0], 1))]
+
+
+# ----------------------------------------------------------------------------
+# (f)4. LIDAR point cloud -> BEV histogram (oatomobile/utils/carla.py:165-233)
+# ----------------------------------------------------------------------------
+def lidar_bev(points, pixels_per_meter: int = 2, hist_max_per_pixel: int = 5, meters_max: int = 50):
+  """utils/carla.py:181-231 — split at z=-2.5 (<= below, >= above), np.histogramdd over
+  linspace(-m, m+1, 2*m*ppm+1) edges, clip at hist_max, divide, stack → [200,200,2] f32."""
+  import numpy as np
+  points = np.asarray(points, dtype=np.float32).reshape(-1, 3)
+  edges = np.linspace(-meters_max, meters_max + 1, meters_max * 2 * pixels_per_meter + 1)
+  feats = []
+  for part in (points[points[..., 2] <= -2.5], points[points[..., 2] >= -2.5]):
+    hist = np.histogramdd(part[..., :2], bins=(edges, edges))[0]
+    hist[hist > hist_max_per_pixel] = hist_max_per_pixel
+    feats.append(hist / hist_max_per_pixel)
+  return np.stack(feats, axis=-1).astype(np.float32)

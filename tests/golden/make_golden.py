@@ -180,9 +180,40 @@ def make_cil():
   print("cil", {k: v.shape for k, v in out.items()})
 
 
+def lidar_points(seed=0, n=20000):
+  """Synthetic point cloud with points on bin edges, on the z split and out of range."""
+  rng = np.random.RandomState(seed)
+  pts = (rng.randn(n, 3) * np.array([18.0, 18.0, 1.5]) + np.array([0.0, 0.0, -2.5])).astype(np.float32)
+  edges = np.linspace(-50, 51, 201)
+  pts[:200, 0] = edges[rng.randint(0, 201, 200)].astype(np.float32)   # exactly (rounded) on edges
+  pts[200:400, 1] = edges[rng.randint(0, 201, 200)].astype(np.float32)
+  pts[400:500, 2] = -2.5                                               # counted in both halves
+  pts[500:520, 0] = 51.0                                               # right-most edge (closed)
+  pts[520:540, 1] = -50.0
+  pts[540:560, 0] = 51.5                                               # out of range
+  pts[560:600, :2] = 3.2                                               # > 5 hits in one bin
+  return pts
+
+
+def make_lidar():
+  from oatomobile.utils import carla as cutil
+
+  class Measurement:
+    pass
+
+  m = Measurement()
+  pts = lidar_points()
+  m.raw_data = pts.tobytes()
+  bev = cutil.carla_lidar_measurement_to_ndarray(m)
+  # stored compactly: levels k/5 as uint8 (exact)
+  np.savez_compressed(os.path.join(HERE, "lidar_bev.npz"), levels=np.round(bev * 5).astype(np.uint8))
+  print("lidar", bev.shape, bev.sum())
+
+
 if __name__ == "__main__":
   torch.set_num_threads(8)
   ref_shim.install()
   for name, cfg in CONFIGS.items():
     make_dim(name, cfg)
   make_cil()
+  make_lidar()

@@ -1,0 +1,78 @@
+"""Loader row: `load_datum` / `as_torch` against the reference's
+own functions when the reference tree is present, and against fixed expectations otherwise."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oatomobile_b200.datasets import CARLADataset, DeviceCollator
+
+
+def _write_samples(tmp_path, n=3):
+  rng = np.random.RandomState(0)
+  for i in range(n):
+    fut = np.cumsum(rng.randn(80, 3) * 0.1 + np.array([0.5 * (i % 2) + 0.02, 0.3 * (i - 1), 0.0]), 0)
+    np.savez_compressed(
+        os.path.join(tmp_path, "%04d.npz" % i),
+        lidar=(rng.rand(200, 200, 2) < 0.1).astype(np.float32) * rng.randint(1, 6, (200, 200, 2)) / 5.0,
+        velocity=rng.randn(3), is_at_traffic_light=np.int64(i % 2),
+        traffic_light_state=np.int64(i % 4), player_future=fut,
+        bird_view_camera_cityscapes=rng.randint(0, 255, (8, 8, 3)).astype(np.uint8))
+  return sorted(os.path.join(tmp_path, f) for f in os.listdir(tmp_path))
+
+
+MODALITIES = ("lidar", "is_at_traffic_light", "traffic_light_state", "player_future", "velocity")
+
+
+def test_load_datum_semantics(tmp_path):
+  files = _write_samples(str(tmp_path))
+  s = CARLADataset.load_datum(files[0], MODALITIES, mode=True, dataformat="CHW")
+  assert s["lidar"].shape == (2, 200, 200) and s["lidar"].dtype == np.float32
+  assert s["is_at_traffic_light"].shape == (1,) and s["velocity"].shape == (3,)
+  assert s["player_future"].shape == (80, 3) and s["mode"].shape == (1,)
+  assert s["name"] == files[0]
+  s2 = CARLADataset.load_datum(files[0], MODALITIES, mode=False, dataformat="HWC")
+  assert s2["lidar"].shape == (200, 200, 2) and "mode" not in s2
+  ds = CARLADataset.as_torch(str(tmp_path), MODALITIES, mode=True)
+  assert len(ds) == 3
+  item = ds[0]
+  assert "name" not in item and all(isinstance(v, np.ndarray) for v in item.values())
+  batch = next(iter(torch.utils.data.DataLoader(ds, batch_size=3)))
+  assert tuple(batch["lidar"].shape) == (3, 2, 200, 200)
+
+
+def test_load_datum_matches_reference(tmp_path):
+  from oracle import ref_shim
+  if not ref_shim.available():
+    pytest.skip("reference tree not present")
+  ref_shim.install()
+  import sys, types
+  for name in ("wget", "tqdm", "absl"):
+    pass
+  try:
+    from oatomobile.datasets.carla import CARLADataset as Ref
+  except Exception as e:  # CARLA-side imports of the module are unavailable here
+    pytest.skip("reference datasets module not importable: %r" % (e,))
+  files = _write_samples(str(tmp_path))
+  for f in files:
+    for fmt in ("HWC", "CHW"):
+      a = CARLADataset.load_datum(f, MODALITIES, mode=True, dataformat=fmt)
+      b = Ref.load_datum(f, MODALITIES, mode=True, dataformat=fmt)
+      assert set(a) == set(b)
+      for k in a:
+        if isinstance(a[k], np.ndarray):
+          assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.gpu
+def test_device_collator_matches_model_transform(tmp_path):
+  import oatomobile_b200 as ob
+  files = _write_samples(str(tmp_path))
+  samples = [CARLADataset.load_datum(f, MODALITIES, mode=True, dataformat="HWC") for f in files]
+  batch = DeviceCollator("cuda:0")(samples)
+  model = ob.ImitativeModel(output_shape=(4, 2))
+  chw = torch.stack([torch.from_numpy(np.transpose(s["lidar"], (2, 0, 1))) for s in samples]).cuda()
+  ref = model.transform({"lidar": chw})["visual_features"]
+  assert torch.equal(batch["visual_features"], ref)
+  assert tuple(batch["player_future"].shape) == (3, 80, 3)
