@@ -11,7 +11,7 @@ from typing import Dict, Mapping, Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboat_b200.so")
+LIB_PATH = os.environ.get("OAT_B200_LIB", os.path.join(_HERE, "liboat_b200.so"))
 
 KIND_DIM, KIND_CIL, KIND_FLOW = 0, 1, 2
 ALGORITHMS = {"WCM": 0, "BCM": 1, "MA": 2}

@@ -293,28 +293,42 @@ __global__ void __launch_bounds__(128) dw_kernel(const __grid_constant__ PtrTabl
                    ? __ldg(reinterpret_cast<const float4*>(src + ((int64_t)(ih0 + r) * Hin + iw) * C))
                    : zero;
   };
-  float4 L[3], M[3], R[3];
-  ldcol(-1, L);  // left padding column
-  if (STRIDE == 1) ldcol(0, M);
-  for (int ow = 0; ow < Hout; ++ow) {
-    if (STRIDE == 1) {
-      ldcol(ow + 1, R);
-    } else {
-      ldcol(2 * ow, M);
-      ldcol(2 * ow + 1, R);
-    }
+  auto emit = [&](int ow, const float4 (&A)[3], const float4 (&Bc)[3], const float4 (&Cc)[3]) {
     float4 acc = bv;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      acc = fma4(L[r], k[3 * r + 0], acc);
-      acc = fma4(M[r], k[3 * r + 1], acc);
-      acc = fma4(R[r], k[3 * r + 2], acc);
+      acc = fma4(A[r], k[3 * r + 0], acc);
+      acc = fma4(Bc[r], k[3 * r + 1], acc);
+      acc = fma4(Cc[r], k[3 * r + 2], acc);
     }
     acc.x = relu6f(acc.x); acc.y = relu6f(acc.y); acc.z = relu6f(acc.z); acc.w = relu6f(acc.w);
     *reinterpret_cast<float4*>(dst + (int64_t)ow * C) = acc;
+  };
+  // Two outputs per iteration: all 6 (stride 1) / 12 (stride 2) column loads of the pair are
+  // issued before the first FMA, so each thread keeps them in flight together.
+  float4 q0[3], q1[3], q2[3], q3[3], q4[3];
+  if (STRIDE == 1) {
+    ldcol(-1, q0);
+    ldcol(0, q1);
+    for (int ow = 0; ow < Hout; ow += 2) {
+      ldcol(ow + 1, q2);
+      ldcol(ow + 2, q3);
+      emit(ow, q0, q1, q2);
+      if (ow + 1 < Hout) emit(ow + 1, q1, q2, q3);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      if (STRIDE == 1) { L[r] = M[r]; M[r] = R[r]; } else { L[r] = R[r]; }
+      for (int r = 0; r < 3; ++r) { q0[r] = q2[r]; q1[r] = q3[r]; }
+    }
+  } else {
+    ldcol(-1, q0);
+    for (int ow = 0; ow < Hout; ow += 2) {
+      ldcol(2 * ow, q1);
+      ldcol(2 * ow + 1, q2);
+      ldcol(2 * ow + 2, q3);
+      ldcol(2 * ow + 3, q4);
+      emit(ow, q0, q1, q2);
+      if (ow + 1 < Hout) emit(ow + 1, q2, q3, q4);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) q0[r] = q4[r];
     }
   }
 }

@@ -15,7 +15,13 @@
 // issuing the 16 small correction MMAs (h_lo.W_hi, h_hi.W_lo) before the 8 main ones.
 //
 // Roles: warps 0-15 compute (warp w: TMEM lanes 32*(w%4).., hidden units 16*(w/4)..),
-// warp 16 = TMEM allocator + single-thread MMA issuer.  The recurrent MMA of step t+1
+// warp 16 = TMEM allocator + single-thread MMA issuer.
+// Latency hiding: the 128-row tile is run as two phase-shifted half tiles (rows 0-63 =
+// lane quadrants 0,1; rows 64-127 = quadrants 2,3) with their own accumulators (2 x 224
+// TMEM columns) and barriers.  Each half's products are issued as full M=128 MMAs over
+// the shared state tile (the other half's rows yield results nobody reads), so while one
+// half waits for its recurrent GEMM the other half runs its gate math: the tensor pipe
+// goes from ~28 % to ~busy and the step time roughly halves, at no extra shared memory.  The recurrent MMA of step t+1
 // is issued right after h_t is published, so it overlaps the head/flow update of t.
 #include <cstring>
 
@@ -146,7 +152,7 @@ __device__ __forceinline__ uint32_t tf32_lo(float v, uint32_t hi) {
 template <int MODE>
 __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_constant__ FlowTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[3];
+  __shared__ uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
   const int model = blockIdx.y;
   if (model == a.skip_model) return;
@@ -157,20 +163,23 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
   const int T = a.T, T2 = 2 * a.T;
   const int64_t row0 = (int64_t)blockIdx.x * TR;
   const int rows_here = (int)min((int64_t)TR, a.N - row0);
-  const uint32_t bar_h = smem_u32(&bars[0]);   // h_t published (512 arrivals)
-  const uint32_t bar_d = smem_u32(&bars[1]);   // recurrent accumulator ready (commit)
-  const uint32_t bar_d2 = smem_u32(&bars[2]);  // head accumulator ready (commit)
+  // per half tile hb in {0,1}: h_t published (256 arrivals) | recurrent acc ready | head acc ready
+  auto bar_h_of = [&](int hb) { return smem_u32(&bars[3 * hb + 0]); };
+  auto bar_d_of = [&](int hb) { return smem_u32(&bars[3 * hb + 1]); };
+  auto bar_d2_of = [&](int hb) { return smem_u32(&bars[3 * hb + 2]); };
 
   if (tid == 0) {
-    mbar_init(bar_h, TCOMPUTE);
-    mbar_init(bar_d, 1);
-    mbar_init(bar_d2, 1);
+    for (int hb = 0; hb < 2; ++hb) {
+      mbar_init(bar_h_of(hb), TCOMPUTE / 2);
+      mbar_init(bar_d_of(hb), 1);
+      mbar_init(bar_d2_of(hb), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_slot)),
-                 "r"(256)
+                 "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -230,19 +239,30 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
           for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, dHh + 2 * ks, dWh + 2 * ks, idesc, 1u);
         }
       };
-      // event e = 0: h_0 = z published;  e = t+1: h_t published
-      mbar_wait(bar_h, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue(tmem, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh);
-      umma_commit(bar_d);
-      for (int t = 0; t < T; ++t) {
-        mbar_wait(bar_h, (uint32_t)((t + 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue(tmem + 192, sbase + OFF_W1HI, sbase + OFF_W1LO, kW1_BYTES, idesc_hd);
-        umma_commit(bar_d2);
-        if (t + 1 < T) {  // next step's recurrent product overlaps this step's head/flow update
-          issue(tmem, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh);
-          umma_commit(bar_d);
+      // Per half tile: event 0 = h_0 published -> recurrent GEMM of step 0; event t+1 = h_t
+      // published -> head GEMM of step t, then the recurrent GEMM of step t+1.  The two
+      // halves are polled round-robin so whichever published first is served first.
+      int ev[2] = {0, 0};
+      while (ev[0] <= T || ev[1] <= T) {
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          if (ev[hb] > T) continue;
+          if (!mbar_try_wait(bar_h_of(hb), (uint32_t)(ev[hb] & 1))) continue;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d0 = tmem + (uint32_t)(hb * 256);
+          if (ev[hb] == 0) {
+            issue(d0, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh);
+            umma_commit(bar_d_of(hb));
+          } else {
+            const int t = ev[hb] - 1;
+            issue(d0 + 192, sbase + OFF_W1HI, sbase + OFF_W1LO, kW1_BYTES, idesc_hd);
+            umma_commit(bar_d2_of(hb));
+            if (t + 1 < T) {
+              issue(d0, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh);
+              umma_commit(bar_d_of(hb));
+            }
+          }
+          ++ev[hb];
         }
       }
     }
@@ -250,7 +270,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
     // ===================== compute warps =====================
     const int q = warp & 3, ug = warp >> 2;        // lane quadrant, unit group (16 units)
     const int row = q * 32 + lane;
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const int hb = q >> 1;                          // half tile of this lane quadrant
+    const uint32_t bar_h = bar_h_of(hb), bar_d = bar_d_of(hb), bar_d2 = bar_d2_of(hb);
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hb * 256);
     const float* gate = reinterpret_cast<const float*>(sptr + OFF_GATE);
     const float* B1 = reinterpret_cast<const float*>(sptr + OFF_B1);
     const float* W2 = reinterpret_cast<const float*>(sptr + OFF_W2);
@@ -392,7 +414,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 512;" ::: "memory");  // y_t visible to all 16 compute warps
+      // y_t visible to the 8 compute warps of this half tile
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + hb) : "memory");
     }
 
     if (hf == 0 && row < rows_here) {
@@ -420,7 +443,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
   }
   if (warp == 16) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512)
                  : "memory");
   }
 }

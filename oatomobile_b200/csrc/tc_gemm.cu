@@ -142,6 +142,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
 // K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart).
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -328,22 +338,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {
           const int c = c0 + hc * 16;
-          float v[16], u[16];
-          tmem_ld16(taddr + (uint32_t)c, v);  // warp-wide: executed by all 32 lanes
-          for (int j = 1; j < used; ++j) {    // partial main products, round-to-nearest adds
-            tmem_ld16(taddr + (uint32_t)(j * BN + c), u);
+          // main[0] and the correction tile are fetched together (one wait), bias in flight
+          const int n = n0 + c;
+          float4 bq[4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += u[i];
+          for (int j = 0; j < 4; ++j)
+            bq[j] = (n + 4 * j < a.N) ? __ldg(reinterpret_cast<const float4*>(bias + n + 4 * j))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          float v[16], u[16];
+          {
+            uint32_t r0[16], r1[16];
+            tmem_ld16_nowait(taddr + (uint32_t)c, r0);  // warp-wide: executed by all 32 lanes
+            tmem_ld16_nowait(taddr + (uint32_t)(C * BN + c), r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r0[i]); u[i] = __uint_as_float(r1[i]); }
           }
-          tmem_ld16(taddr + (uint32_t)(C * BN + c), u);  // correction terms
+          for (int j = 1; j < used; ++j) {    // partial main products, round-to-nearest adds
+            float w[16];
+            tmem_ld16(taddr + (uint32_t)(j * BN + c), w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += u[i];
-          const int n = n0 + c;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             if (n + j < a.N) {  // N is a multiple of 4: float4 groups are all-or-nothing
-              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n + j));
+              const float4 b = bq[j >> 2];
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
               if (a.relu6) { o.x = relu6f(o.x); o.y = relu6f(o.y); o.z = relu6f(o.z); o.w = relu6f(o.w); }
               if (rrow) {

@@ -196,7 +196,7 @@ class HostRIPPipeline:
         d2h += out[k].numel() * out[k].element_size()
     compute.synchronize()  # results are now valid on the host
     self.h2d_bytes, self.d2h_bytes = h2d, d2h
-    return dict(self._host_out)
+    return {k: self._host_out[k] for k in ("plan", "kstar", "sbest")}
 
   def stream(self, batches, epsilon: float = 1.0):
     """Streaming form for a continuous feed of batches (an agent fleet / a replay): yields
