@@ -14,14 +14,8 @@
 // Truncation of the tensor core's accumulate is kept at 8 MMAs per accumulator by
 // issuing the 16 small correction MMAs (h_lo.W_hi, h_hi.W_lo) before the 8 main ones.
 //
-// Roles: warps 0-15 compute (warp w: TMEM lanes 32*(w%4).., hidden units 16*(w/4)..),
-// warp 16 = TMEM allocator + single-thread MMA issuer.
-// Latency hiding: the 128-row tile is run as two phase-shifted half tiles (rows 0-63 =
-// lane quadrants 0,1; rows 64-127 = quadrants 2,3) with their own accumulators (2 x 224
-// TMEM columns) and barriers.  Each half's products are issued as full M=128 MMAs over
-// the shared state tile (the other half's rows yield results nobody reads), so while one
-// half waits for its recurrent GEMM the other half runs its gate math: the tensor pipe
-// goes from ~28 % to ~busy and the step time roughly halves, at no extra shared memory.  The recurrent MMA of step t+1
+// Roles: warps 0-7 compute (warp w: TMEM lanes 32*(w%4).., hidden units 32*(w/4)..),
+// warp 8 = TMEM allocator + single-thread MMA issuer.  The recurrent MMA of step t+1
 // is issued right after h_t is published, so it overlaps the head/flow update of t.
 #include <cstring>
 
@@ -31,8 +25,7 @@ namespace oat {
 namespace {
 
 constexpr int TR = 128;                 // rows per CTA
-constexpr int TTHREADS = 544;           // 16 compute warps + 1 MMA warp
-constexpr int TCOMPUTE = 512;
+constexpr int TTHREADS = 288;           // 8 compute warps + 1 MMA warp
 constexpr int kH_BYTES = TR * 128;      // one k-block (32 fp32) of the state tile: 16 KB
 constexpr int kW_BYTES = 192 * 128;     // one k-block of W_hh: 24 KB
 constexpr int kW1_BYTES = 32 * 128;     // one k-block of W_1: 4 KB
@@ -152,7 +145,7 @@ __device__ __forceinline__ uint32_t tf32_lo(float v, uint32_t hi) {
 template <int MODE>
 __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_constant__ FlowTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[6];
+  __shared__ uint64_t bars[3];
   __shared__ uint32_t tmem_slot;
   const int model = blockIdx.y;
   if (model == a.skip_model) return;
@@ -163,23 +156,20 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
   const int T = a.T, T2 = 2 * a.T;
   const int64_t row0 = (int64_t)blockIdx.x * TR;
   const int rows_here = (int)min((int64_t)TR, a.N - row0);
-  // per half tile hb in {0,1}: h_t published (256 arrivals) | recurrent acc ready | head acc ready
-  auto bar_h_of = [&](int hb) { return smem_u32(&bars[3 * hb + 0]); };
-  auto bar_d_of = [&](int hb) { return smem_u32(&bars[3 * hb + 1]); };
-  auto bar_d2_of = [&](int hb) { return smem_u32(&bars[3 * hb + 2]); };
+  const uint32_t bar_h = smem_u32(&bars[0]);   // h_t published (256 arrivals)
+  const uint32_t bar_d = smem_u32(&bars[1]);   // recurrent accumulator ready (commit)
+  const uint32_t bar_d2 = smem_u32(&bars[2]);  // head accumulator ready (commit)
 
   if (tid == 0) {
-    for (int hb = 0; hb < 2; ++hb) {
-      mbar_init(bar_h_of(hb), TCOMPUTE / 2);
-      mbar_init(bar_d_of(hb), 1);
-      mbar_init(bar_d2_of(hb), 1);
-    }
+    mbar_init(bar_h, 256);
+    mbar_init(bar_d, 1);
+    mbar_init(bar_d2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 16) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_slot)),
-                 "r"(512)
+                 "r"(256)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -208,7 +198,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 16) {
+  if (warp == 8) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // weight image -> async proxy
@@ -239,56 +229,40 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
           for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, dHh + 2 * ks, dWh + 2 * ks, idesc, 1u);
         }
       };
-      // Per half tile: event 0 = h_0 published -> recurrent GEMM of step 0; event t+1 = h_t
-      // published -> head GEMM of step t, then the recurrent GEMM of step t+1.  The two
-      // halves are polled round-robin so whichever published first is served first.
-      int ev[2] = {0, 0};
-      while (ev[0] <= T || ev[1] <= T) {
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          if (ev[hb] > T) continue;
-          if (!mbar_try_wait(bar_h_of(hb), (uint32_t)(ev[hb] & 1))) continue;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t d0 = tmem + (uint32_t)(hb * 256);
-          if (ev[hb] == 0) {
-            issue(d0, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh);
-            umma_commit(bar_d_of(hb));
-          } else {
-            const int t = ev[hb] - 1;
-            issue(d0 + 192, sbase + OFF_W1HI, sbase + OFF_W1LO, kW1_BYTES, idesc_hd);
-            umma_commit(bar_d2_of(hb));
-            if (t + 1 < T) {
-              issue(d0, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh);
-              umma_commit(bar_d_of(hb));
-            }
-          }
-          ++ev[hb];
+      // event e = 0: h_0 = z published;  e = t+1: h_t published
+      mbar_wait(bar_h, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue(tmem, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh);
+      umma_commit(bar_d);
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(bar_h, (uint32_t)((t + 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue(tmem + 192, sbase + OFF_W1HI, sbase + OFF_W1LO, kW1_BYTES, idesc_hd);
+        umma_commit(bar_d2);
+        if (t + 1 < T) {  // next step's recurrent product overlaps this step's head/flow update
+          issue(tmem, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh);
+          umma_commit(bar_d);
         }
       }
     }
   } else {
     // ===================== compute warps =====================
-    const int q = warp & 3, ug = warp >> 2;        // lane quadrant, unit group (16 units)
+    const int q = warp & 3, hf = warp >> 2;
     const int row = q * 32 + lane;
-    const int hb = q >> 1;                          // half tile of this lane quadrant
-    const uint32_t bar_h = bar_h_of(hb), bar_d = bar_d_of(hb), bar_d2 = bar_d2_of(hb);
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hb * 256);
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const float* gate = reinterpret_cast<const float*>(sptr + OFF_GATE);
     const float* B1 = reinterpret_cast<const float*>(sptr + OFF_B1);
     const float* W2 = reinterpret_cast<const float*>(sptr + OFF_W2);
     const float* B2 = reinterpret_cast<const float*>(sptr + OFF_B2);
     float* yprev = reinterpret_cast<float*>(sptr + OFF_YPREV);
     float* io = reinterpret_cast<float*>(sptr + OFF_IO);
-    // units 16*ug .. +15 live in k-block ug/2, 16-byte chunks (ug%2)*4 .. +3 of the row
-    const uint32_t hhi_row = sbase + OFF_HHI + (ug >> 1) * kH_BYTES + row * 128;
-    const uint32_t hlo_row = sbase + OFF_HLO + (ug >> 1) * kH_BYTES + row * 128;
-    const int hf = ug;  // "half 0" below = the four warps with ug == 0 (they own one row each)
+    const uint32_t hhi_row = sbase + OFF_HHI + hf * kH_BYTES + row * 128;
+    const uint32_t hlo_row = sbase + OFF_HLO + hf * kH_BYTES + row * 128;
 
-    auto publish_h = [&](const float (&h)[16]) {
+    auto publish_h = [&](const float (&h)[32]) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t chunk = (uint32_t)((ug & 1) * 4 + c);
-        const uint32_t off = (chunk ^ (uint32_t)(row & 7)) << 4;  // SWIZZLE_128B: chunk ^= row % 8
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t off = (uint32_t)((c ^ (row & 7)) << 4);  // SWIZZLE_128B: chunk ^= row % 8
         const uint32_t h0 = tf32_hi(h[4 * c]), h1 = tf32_hi(h[4 * c + 1]),
                        h2 = tf32_hi(h[4 * c + 2]), h3 = tf32_hi(h[4 * c + 3]);
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(hhi_row + off), "r"(h0),
@@ -304,55 +278,52 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
       mbar_arrive(bar_h);
     };
 
-    // h_0 = z[row / rows_per_z], this thread's 16 hidden units
-    float h[16];
+    // h_0 = z[row / rows_per_z], this thread's 32 hidden units
+    float h[32];
     {
       const float* zb = a.z + (int64_t)model * a.z_model_stride;
       if (row < rows_here) {
-        const float4* zr = reinterpret_cast<const float4*>(zb + ((row0 + row) / a.rows_per_z) * kHidden + ug * 16);
+        const float4* zr = reinterpret_cast<const float4*>(zb + ((row0 + row) / a.rows_per_z) * kHidden + hf * 32);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 8; ++c) {
           const float4 v = __ldg(zr + c);
           h[4 * c] = v.x; h[4 * c + 1] = v.y; h[4 * c + 2] = v.z; h[4 * c + 3] = v.w;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) h[i] = 0.0f;
+        for (int i = 0; i < 32; ++i) h[i] = 0.0f;
       }
     }
     publish_h(h);
 
     float sumsq = 0.0f, sumlog = 0.0f, goal_ll = 0.0f;
     for (int t = 0; t < T; ++t) {
-      // ---- gates: r|z|n pre-activations from TMEM columns [g*64 + ug*16, +16) ------------
+      // ---- gates: r|z|n pre-activations from TMEM columns [g*64 + hf*32, +32) -----------
       mbar_wait(bar_d, (uint32_t)(t & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const float2 yp = *reinterpret_cast<const float2*>(yprev + 2 * row);
-      {
+#pragma unroll
+      for (int half16 = 0; half16 < 2; ++half16) {
         uint32_t ar[16], az[16], an[16];
-        const uint32_t col = (uint32_t)(ug * 16);
+        const uint32_t col = (uint32_t)(hf * 32 + half16 * 16);
         tmem_ld16_nowait(trow + col, ar);
         tmem_ld16_nowait(trow + 64 + col, az);
         tmem_ld16_nowait(trow + 128 + col, an);
         tmem_wait_ld();
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const int j = ug * 16 + u;
+          const int j = hf * 32 + half16 * 16 + u;
           const float4 g0 = *reinterpret_cast<const float4*>(gate + j * 12);      // wr0 wr1 br wz0
           const float4 g1 = *reinterpret_cast<const float4*>(gate + j * 12 + 4);  // wz1 bz wn0 wn1
           const float2 g2 = *reinterpret_cast<const float2*>(gate + j * 12 + 8);  // bin bhn
           const float ir = fmaf(g0.y, yp.y, fmaf(g0.x, yp.x, g0.z));
           const float iz = fmaf(g1.x, yp.y, fmaf(g0.w, yp.x, g1.y));
           const float in_ = fmaf(g1.w, yp.y, fmaf(g1.z, yp.x, g2.x));
-          // r = 1/(1+e^-a), g = 1/(1+e^-b) with ONE reciprocal: 1/(A*B) * B, 1/(A*B) * A
-          // (exponent clamped at 40 so ea*eb stays finite; sigmoid(-40) = 4e-18 either way)
-          const float ea = 1.0f + __expf(fminf(-(ir + __uint_as_float(ar[u])), 40.0f));
-          const float eb = 1.0f + __expf(fminf(-(iz + __uint_as_float(az[u])), 40.0f));
-          const float inv = __fdividef(1.0f, ea * eb);
-          const float rr = inv * eb;
-          const float gg = inv * ea;
+          const float rr = sigmoid_fast(ir + __uint_as_float(ar[u]));
+          const float gg = sigmoid_fast(iz + __uint_as_float(az[u]));
           const float nn = tanh_fast(fmaf(rr, __uint_as_float(an[u]) + g2.y, in_));
-          h[u] = fmaf(gg, h[u] - nn, nn);
+          const int hi = half16 * 16 + u;
+          h[hi] = fmaf(gg, h[hi] - nn, nn);
         }
       }
       publish_h(h);  // -> head MMA of step t and recurrent MMA of step t+1
@@ -414,8 +385,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       }
-      // y_t visible to the 8 compute warps of this half tile
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + hb) : "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // y_t visible to all 8 compute warps
     }
 
     if (hf == 0 && row < rows_here) {
@@ -441,9 +411,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
       for (int i = tid; i < n; i += TTHREADS) dst[i] = io[i];
     }
   }
-  if (warp == 16) {
+  if (warp == 8) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256)
                  : "memory");
   }
 }

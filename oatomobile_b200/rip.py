@@ -200,36 +200,24 @@ class HostRIPPipeline:
 
   def stream(self, batches, epsilon: float = 1.0):
     """Streaming form for a continuous feed of batches (an agent fleet / a replay): yields
-    the host results of batch i while the pinned inputs of batch i+1 are already being
-    uploaded on the copy stream (double-buffered device inputs).  Every batch is still
-    copied H2D from pinned memory and its plans are read back D2H; only the waiting is
-    overlapped with the kernels of the previous batch."""
+    the host results of batch i while batch i+1 is already uploaded AND enqueued (inputs
+    double-buffered on the device, results double-buffered in pinned memory), so neither the
+    PCIe copies nor the host-side launch work of the next batch are exposed.  Every batch is
+    still copied H2D from pinned memory and its plans are read back D2H."""
     compute = torch.cuda.current_stream(self._device)
     for ev in self._consumed:
       ev.record(compute)
     it = iter(batches)
-    try:
-      cur = next(it)
-    except StopIteration:
-      return
-    B = cur["lidar"].shape[0]
-    self.h2d_bytes = self._upload(cur, 0, B, 0)
-    i = 0
-    while cur is not None:
-      slot = i & 1
-      try:
-        nxt = next(it)
-      except StopIteration:
-        nxt = None
-      if nxt is not None:
-        self._upload(nxt, 0, nxt["lidar"].shape[0], slot ^ 1)
+
+    def enqueue(batch, slot):
+      """upload + score + async D2H of one batch; returns (results, done event)."""
+      h2d = self._upload(batch, 0, batch["lidar"].shape[0], slot)
       compute.wait_event(self._uploaded[slot])
       d = dict(self._dev[slot])
       x, goal = d.pop("x"), d.pop("goal")
       out = self._scorer(x=x, goal=goal, epsilon=epsilon, **d)
       self._consumed[slot].record(compute)
-      d2h = 0
-      res = {}
+      d2h, res = 0, {}
       for k in ("plan", "kstar", "sbest"):
         t = out[k]
         hb = self._host_out.get((k, slot))
@@ -241,7 +229,17 @@ class HostRIPPipeline:
         res[k] = hb
       done = torch.cuda.Event()
       done.record(compute)
-      self.d2h_bytes = d2h
-      done.synchronize()  # this batch's plans are on the host; the next upload keeps running
-      yield res
-      cur, i = nxt, i + 1
+      self.h2d_bytes, self.d2h_bytes = h2d, d2h
+      return res, done
+
+    pending = None
+    i = 0
+    for batch in it:
+      cur = enqueue(batch, i & 1)
+      if pending is not None:
+        pending[1].synchronize()  # batch i-1 is on the host; batch i keeps the GPU busy
+        yield pending[0]
+      pending, i = cur, i + 1
+    if pending is not None:
+      pending[1].synchronize()
+      yield pending[0]

@@ -132,6 +132,51 @@ def _worker(rank, world, port, algo, out_path):
   dist.destroy_process_group()
 
 
+def _worker_groups(rank, world, port, out_path):
+  """bench.py's layout beyond E ranks: world 4, E = 2 -> two replica groups of 2 ranks, each
+  group scoring its own scenes; collectives stay inside the group."""
+  sys.path.insert(0, ROOT)
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  torch.set_num_threads(1)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  _install_cpu_ops()
+  from oracle import restatement as R
+  from oatomobile_b200.rip import RIPScorer
+  from oatomobile_b200.synthetic import synthetic_inputs, synthetic_state_dict
+  E2 = 2
+  gsize = min(world, E2)
+  group_id, grank = rank // gsize, rank % gsize
+  group = None
+  for g in range(world // gsize):
+    pg = dist.new_group(list(range(g * gsize, (g + 1) * gsize)))
+    if g == group_id:
+      group = pg
+  sds = [synthetic_state_dict("dim", C, 800 + m) for m in range(E2)]
+  inp = synthetic_inputs(2, C, K, T, seed=10 + group_id)  # each group has its own scenes
+  scorer = RIPScorer([_FakeModel(sds[grank])], "WCM", group=group,
+                     proposal_model=None if grank == 0 else _FakeModel(sds[0]))
+  with torch.no_grad():
+    vis = R.transform_visual(inp["lidar"])
+    out = scorer(x=inp["x"], goal=inp["goal"], epsilon=1.0, visual_features=vis,
+                 velocity=inp["velocity"], is_at_traffic_light=inp["is_at_traffic_light"],
+                 traffic_light_state=inp["traffic_light_state"])
+    ref = R.rip_score_from_inputs(sds, inp["lidar"], inp["velocity"], inp["is_at_traffic_light"],
+                                  inp["traffic_light_state"], inp["x"], inp["goal"], 1.0, "WCM")
+  ok = torch.equal(out["q"], ref["q"]) and torch.equal(out["kstar"].long(), ref["kstar"])
+  t = torch.tensor([1.0 if ok else 0.0])
+  dist.all_reduce(t, op=dist.ReduceOp.MIN)  # global collective still works next to the groups
+  torch.save({"ok": bool(t.item() == 1.0)}, out_path % rank)
+  dist.destroy_process_group()
+
+
+def test_two_replica_groups_world4(tmp_path):
+  world = 4
+  out_path = str(tmp_path / "rank%d.pt")
+  mp.spawn(_worker_groups, args=(world, _free_port(), out_path), nprocs=world, join=True)
+  assert all(torch.load(out_path % r)["ok"] for r in range(world))
+
+
 @pytest.mark.parametrize("algo", ["WCM", "MA"])
 def test_sharded_scorer_world2_matches_single_process(tmp_path, algo):
   world = 2
