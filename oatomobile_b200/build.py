@@ -34,27 +34,32 @@ def _stale():
   return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-  if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+  """`defines` / `out` build an experimental variant next to the product library
+  (select it at run time with OAT_B200_LIB=<path>)."""
+  if out is None and not defines and not force and not _stale():
     return LIB
   objs = []
   procs = []
   os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
   for src in SOURCES:
     obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-c", os.path.join(CSRC, src), "-o", obj]
+    if out is not None:
+      obj = obj.replace(".o", "." + os.path.basename(out) + ".o")
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (
+        ["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     objs.append(obj)
   for src, p in procs:
-    out, _ = p.communicate()
+    log, _ = p.communicate()
     if verbose or p.returncode != 0:
-      sys.stderr.write(out.decode())
+      sys.stderr.write(log.decode())
     if p.returncode != 0:
       raise RuntimeError("nvcc failed on %s" % src)
-  link = [_nvcc(), "-shared", "-cudart", "static", "-o", LIB] + objs
+  target = out or LIB
+  link = [_nvcc(), "-shared", "-cudart", "static", "-o", target] + objs
   subprocess.check_call(link)
-  return LIB
+  return target
 
 
 if __name__ == "__main__":

@@ -261,8 +261,11 @@ __device__ __forceinline__ float4 fma4(const float4 v, const float4 k, const flo
                      fmaf(v.w, k.w, acc.w));
 }
 
+#ifndef OAT_DW_THREADS
+#define OAT_DW_THREADS 128
+#endif
 template <int STRIDE>
-__global__ void __launch_bounds__(128) dw_kernel(const __grid_constant__ PtrTable w,
+__global__ void __launch_bounds__(OAT_DW_THREADS) dw_kernel(const __grid_constant__ PtrTable w,
                                                  const __grid_constant__ PtrTable bias,
                                                  const float* __restrict__ in,
                                                  float* __restrict__ out, int B, int Hin,
@@ -453,11 +456,11 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       PtrTable w = table([bi](const OatModel* m) { return m->blocks[bi].dw.w; });
       PtrTable b = table([bi](const OatModel* m) { return m->blocks[bi].dw.b; });
       const int64_t total = (int64_t)B * blk.hout * (blk.hid / 4);
-      dim3 grid((unsigned)((total + 127) / 128), E);
+      dim3 grid((unsigned)((total + OAT_DW_THREADS - 1) / OAT_DW_THREADS), E);
       if (blk.stride == 1)
-        dw_kernel<1><<<grid, 128, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid);
+        dw_kernel<1><<<grid, OAT_DW_THREADS, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid);
       else
-        dw_kernel<2><<<grid, 128, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid);
+        dw_kernel<2><<<grid, OAT_DW_THREADS, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid);
       OAT_LAUNCH_CHECK();
     }
     {  // project 1x1 + BN (linear) + residual

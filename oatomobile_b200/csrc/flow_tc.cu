@@ -319,8 +319,18 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc_kernel(const __grid_const
           const float ir = fmaf(g0.y, yp.y, fmaf(g0.x, yp.x, g0.z));
           const float iz = fmaf(g1.x, yp.y, fmaf(g0.w, yp.x, g1.y));
           const float in_ = fmaf(g1.w, yp.y, fmaf(g1.z, yp.x, g2.x));
+#ifdef OAT_FLOW_SHARED_RCP
+          // r = 1/A, g = 1/B from ONE reciprocal: inv = 1/(A*B); r = inv*B, g = inv*A
+          // (exponent clamped at 40 so A*B stays finite; sigmoid(-40) = 4e-18 either way)
+          const float ea = 1.0f + __expf(fminf(-(ir + __uint_as_float(ar[u])), 40.0f));
+          const float eb = 1.0f + __expf(fminf(-(iz + __uint_as_float(az[u])), 40.0f));
+          const float inv = __fdividef(1.0f, ea * eb);
+          const float rr = inv * eb;
+          const float gg = inv * ea;
+#else
           const float rr = sigmoid_fast(ir + __uint_as_float(ar[u]));
           const float gg = sigmoid_fast(iz + __uint_as_float(az[u]));
+#endif
           const float nn = tanh_fast(fmaf(rr, __uint_as_float(an[u]) + g2.y, in_));
           const int hi = half16 * 16 + u;
           h[hi] = fmaf(gg, h[hi] - nn, nn);

@@ -49,7 +49,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // 32 fp32 = 128 B = one swizzle atom row
 constexpr int TC_THREADS = 448;  // 8 epilogue + 4 splitter warps + TMA + MMA
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 5;
 constexpr int TC_TMEM_COLS = 512;
 
 struct TcArgs {
@@ -65,6 +65,7 @@ struct TcArgs {
   int BN, n_tiles, m_tiles, stages;
   int chunks;  // main accumulators per tile (k-blocks round-robin); +1 correction buffer
   int nbuf;    // 1 or 2 accumulator groups (tile double-buffering when TMEM allows)
+  int wres;    // 1: the model's whole W_hi/W_lo stays resident in smem, stages hold only A
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -112,7 +113,6 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
           reinterpret_cast<uint64_t>(map)),
       "r"(c0), "r"(c1), "r"(c2), "r"(src)
       : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -167,7 +167,7 @@ __device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.0f), 
 
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[4 * TC_MAX_STAGES + 4];
+  __shared__ uint64_t bars[4 * TC_MAX_STAGES + 6];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -175,12 +175,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
   const int S = a.stages;
   const int BN = a.BN;
   const uint32_t w_bytes = (uint32_t)BN * 128u;
-  const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * w_bytes;
-  auto sA = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
+  const int k_blocks_all = (a.K + TC_BK - 1) / TC_BK;
+  // resident-W mode: [W_hi k-blocks][W_lo k-blocks] first, then A-only stages
+  const uint32_t wres_bytes = a.wres ? 2u * (uint32_t)k_blocks_all * w_bytes : 0u;
+  const uint32_t stage_bytes = 2u * TC_A_BYTES + (a.wres ? 0u : 2u * w_bytes);
+  auto sA = [&](int s) { return smem_base + wres_bytes + (uint32_t)s * stage_bytes; };
   auto sAl = [&](int s) { return sA(s) + TC_A_BYTES; };
   auto sWh = [&](int s) { return sA(s) + 2u * TC_A_BYTES; };
   auto sWl = [&](int s) { return sWh(s) + w_bytes; };
-  const uint32_t stage_out = smem_base + (uint32_t)S * stage_bytes;  // 2 x 16 KB store staging
+  const uint32_t stage_out = smem_base + wres_bytes + (uint32_t)S * stage_bytes;  // 2 x 16 KB store staging
+  auto rWh = [&](int kb) { return smem_base + (uint32_t)kb * w_bytes; };
+  auto rWl = [&](int kb) { return smem_base + (uint32_t)(k_blocks_all + kb) * w_bytes; };
+  const uint32_t bar_wfull = smem_u32(&bars[4 * TC_MAX_STAGES + 4]);   // resident W landed (per model)
+  const uint32_t bar_wfree = smem_u32(&bars[4 * TC_MAX_STAGES + 5]);   // MMAs of the model retired
   auto bar_full = [&](int s) { return smem_u32(&bars[s]); };
   auto bar_split = [&](int s) { return smem_u32(&bars[TC_MAX_STAGES + s]); };
   auto bar_empty = [&](int s) { return smem_u32(&bars[2 * TC_MAX_STAGES + s]); };
@@ -197,6 +204,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
       mbar_init(bar_tfull(i), 1);
       mbar_init(bar_tempty(i), 256);
     }
+    mbar_init(bar_wfull, 1);
+    mbar_init(bar_wfree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 13) {  // TMEM allocation is a warp-wide operation
@@ -224,18 +233,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
   if (warp == 12) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, wgen = 0;
+      int cur_e = -1;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int e = t / tiles_per_model, r = t % tiles_per_model;
         const int m0 = (r / a.n_tiles) * TC_BM, n0 = (r % a.n_tiles) * BN;
+        if (a.wres && e != cur_e) {  // (re)load the whole weight matrix of model e once
+          if (cur_e >= 0) mbar_wait(bar_wfree, (wgen - 1) & 1);  // previous model's MMAs retired
+          mbar_expect_tx(bar_wfull, 2u * (uint32_t)k_blocks * w_bytes);
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            tma_load_3d(rWh(kb), &a.mapWh, bar_wfull, kb * TC_BK, 0, e);
+            tma_load_3d(rWl(kb), &a.mapWl, bar_wfull, kb * TC_BK, 0, e);
+          }
+          cur_e = e;
+          ++wgen;
+        }
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(bar_empty(s), ph ^ 1);
-          mbar_expect_tx(bar_full(s), TC_A_BYTES + 2u * w_bytes);
-          tma_load_3d(sA(s), &a.mapA, bar_full(s), kb * TC_BK, m0, e);
-          tma_load_3d(sWh(s), &a.mapWh, bar_full(s), kb * TC_BK, n0, e);
-          tma_load_3d(sWl(s), &a.mapWl, bar_full(s), kb * TC_BK, n0, e);
+          if (a.wres) {
+            mbar_expect_tx(bar_full(s), TC_A_BYTES);
+            tma_load_3d(sA(s), &a.mapA, bar_full(s), kb * TC_BK, m0, e);
+          } else {
+            mbar_expect_tx(bar_full(s), TC_A_BYTES + 2u * w_bytes);
+            tma_load_3d(sA(s), &a.mapA, bar_full(s), kb * TC_BK, m0, e);
+            tma_load_3d(sWh(s), &a.mapWh, bar_full(s), kb * TC_BK, n0, e);
+            tma_load_3d(sWl(s), &a.mapWl, bar_full(s), kb * TC_BK, n0, e);
+          }
         }
       }
     }
@@ -245,9 +270,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
       // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = BN
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
-      uint32_t it = 0, lt = 0;
+      uint32_t it = 0, lt = 0, wgen = 0;
+      int cur_e = -1;
       const int C = a.chunks;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+        if (a.wres) {
+          const int e = t / tiles_per_model;
+          if (e != cur_e) {
+            if (cur_e >= 0) umma_commit(bar_wfree);  // all MMAs that read the old weights
+            mbar_wait(bar_wfull, wgen & 1);
+            cur_e = e;
+            ++wgen;
+          }
+        }
         const int ab = (a.nbuf == 2) ? (int)(lt & 1) : 0;
         const uint32_t aph = (a.nbuf == 2) ? ((lt >> 1) & 1) : (lt & 1);
         mbar_wait(bar_tempty(ab), aph ^ 1);
@@ -260,7 +295,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
           mbar_wait(bar_split(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t dAh = make_desc_sw128(sA(s)), dAl = make_desc_sw128(sAl(s));
-          const uint64_t dWh = make_desc_sw128(sWh(s)), dWl = make_desc_sw128(sWl(s));
+          const uint64_t dWh = make_desc_sw128(a.wres ? rWh(kb) : sWh(s));
+          const uint64_t dWl = make_desc_sw128(a.wres ? rWl(kb) : sWl(s));
           const int kleft = a.K - kb * TC_BK;
           const int slices = kleft >= TC_BK ? 4 : (kleft + 7) / 8;  // zero-filled k-slices skipped
           const uint32_t d_main = grp + (uint32_t)((kb % C) * BN);
@@ -316,7 +352,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
     const int used = k_blocks < C ? k_blocks : C;  // main accumulators actually written
     const int grp = warp >> 2, qd = warp & 3;      // slab parity, TMEM lane quadrant
     const int et = threadIdx.x & 127;              // thread index inside the group
-    const uint32_t sbuf = stage_out + (uint32_t)grp * (uint32_t)TC_A_BYTES;  // one staging tile per group
+    // two staging tiles per group (ping-pong): the TMA store of slab i drains while slab i+1
+    // is being assembled; measured before: with one tile the store drain (~1 us) serialised
+    // every slab and bounded all memory-bound layers.
+    const uint32_t sbuf0 = stage_out + (uint32_t)(2 * grp) * (uint32_t)TC_A_BYTES;
+    uint32_t slab_it = 0;
     const int bar_id = 2 + grp;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
       const int e = t / tiles_per_model, r = t % tiles_per_model;
@@ -331,9 +371,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * (C + 1) * BN);
       const float* __restrict__ bias = a.bias + (int64_t)e * a.N;
       const float* __restrict__ rrow = (a.R && row_ok) ? a.R + ((int64_t)e * a.M + row) * a.N : nullptr;
-      for (int c0 = grp * 32; c0 < BN; c0 += 64) {
-        // the TMA store that last read this group's staging tile must have drained
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      for (int c0 = grp * 32; c0 < BN; c0 += 64, ++slab_it) {
+        const uint32_t sbuf = sbuf0 + (slab_it & 1) * (uint32_t)TC_A_BYTES;
+        // the TMA store that read this staging tile two slabs ago must have drained
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {
@@ -384,7 +425,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        if (et == 0 && n0 + c0 < a.N) tma_store_3d(&a.mapC, sbuf, n0 + c0, m0, e);
+        if (et == 0) {
+          if (n0 + c0 < a.N) tma_store_3d(&a.mapC, sbuf, n0 + c0, m0, e);
+          // one bulk group per slab, even when the slab lies beyond N and nothing is stored:
+          // `wait_group.read 1` above counts groups, so the ping-pong stays in step.
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(bar_tempty(ab));
@@ -486,21 +532,31 @@ int tc_pw_gemm(const TcGemmProblem& p, cudaStream_t stream) {
   if (a.chunks > 7) a.chunks = 7;
   const int sets = a.chunks + 1;                       // + correction buffer
   int bn_max = ((TC_TMEM_COLS / sets) / 32) * 32;  // (C+1)*BN <= 512 TMEM columns
-  if (bn_max > 224) bn_max = 224;                  // two smem stages + store staging must fit
+#ifndef OAT_TC_BN_CAP
+#define OAT_TC_BN_CAP 160
+#endif
+  if (bn_max > OAT_TC_BN_CAP) bn_max = OAT_TC_BN_CAP;  // >= 2 smem stages + store staging must fit
   a.n_tiles = (p.N + bn_max - 1) / bn_max;
   const int per = (p.N + a.n_tiles - 1) / a.n_tiles;
   a.BN = ((per + 31) / 32) * 32;  // whole 32-column store slabs
   a.nbuf = (2 * sets * a.BN <= TC_TMEM_COLS) ? 2 : 1;
   a.m_tiles = (p.M + TC_BM - 1) / TC_BM;
-  const int stage_bytes = 2 * TC_A_BYTES + 2 * a.BN * 128;
-  a.stages = (216 * 1024 - 2 * TC_A_BYTES) / stage_bytes;  // minus the store staging buffers
+  const int kb_all = (p.K + TC_BK - 1) / TC_BK;
+  const int wres_bytes = 2 * kb_all * a.BN * 128;
+  a.wres = 0;
+#ifdef OAT_TC_WRES
+  // small weight matrices (early, memory-bound layers): keep W resident, stream only A
+  if (a.n_tiles == 1 && wres_bytes <= 64 * 1024) a.wres = 1;
+#endif
+  const int stage_bytes = 2 * TC_A_BYTES + (a.wres ? 0 : 2 * a.BN * 128);
+  a.stages = (216 * 1024 - 4 * TC_A_BYTES - (a.wres ? wres_bytes : 0)) / stage_bytes;  // 4 store-staging tiles
   if (a.stages > TC_MAX_STAGES) a.stages = TC_MAX_STAGES;
   if (a.stages < 2) return fail("tc_pw_gemm: tile does not fit in shared memory");
   if (int rc = make_map(&a.mapA, p.A, p.K, p.M, p.E, TC_BM)) return rc;
   if (int rc = make_map(&a.mapWh, p.Wh, p.K, p.N, p.E, a.BN)) return rc;
   if (int rc = make_map(&a.mapWl, p.Wl, p.K, p.N, p.E, a.BN)) return rc;
   if (int rc = make_map(&a.mapC, p.C, p.N, p.M, p.E, TC_BM)) return rc;
-  const int smem = a.stages * stage_bytes + 2 * TC_A_BYTES + 1024;
+  const int smem = a.stages * stage_bytes + (a.wres ? wres_bytes : 0) + 4 * TC_A_BYTES + 1024;
   static int configured[64] = {0};
   int dev = 0;
   OAT_CUDA(cudaGetDevice(&dev));

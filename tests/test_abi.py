@@ -94,3 +94,25 @@ def test_state_dict_layout():
   assert len(c.state_dict()) == 326
   c.load_state_dict(synthetic_state_dict("cil", 2, 0), strict=True)
   assert tuple(c.state_dict()["_merger._model.0.weight"].shape) == (64, 134)
+
+
+def test_checkpoint_interchange_with_reference(tmp_path):
+  """A checkpoint written by `Checkpointer` loads into the reference class and back
+  (SURVEY.md §8 a16); skipped where the reference tree is absent."""
+  import oatomobile_b200 as ob
+  from oatomobile_b200.savers import Checkpointer
+  from oatomobile_b200.synthetic import synthetic_state_dict
+  model = ob.ImitativeModel(output_shape=(4, 2))
+  model.load_state_dict(synthetic_state_dict("dim", 2, 5))
+  path = Checkpointer(model, str(tmp_path)).save(epoch=3)
+  assert path.endswith("model-3.pt")
+  other = ob.ImitativeModel(output_shape=(4, 2))
+  Checkpointer(other, str(tmp_path)).load(epoch=3)
+  assert all(torch.equal(a, b) for a, b in zip(model.state_dict().values(),
+                                               other.state_dict().values()))
+  from oracle import ref_shim
+  if ref_shim.available():
+    ref = ref_shim.make_imitative_model(T=4, in_channels=2, seed=0, randomize_bn=False)
+    ref.load_state_dict(torch.load(path), strict=True)          # ours -> reference
+    torch.save(ref.state_dict(), str(tmp_path / "ref.pt"))
+    other.load_state_dict(torch.load(str(tmp_path / "ref.pt")), strict=True)  # reference -> ours
