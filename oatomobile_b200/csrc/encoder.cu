@@ -64,6 +64,61 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_kernel(
   for (int i = threadIdx.x; i < 9 * C * 32; i += STEM_THREADS) ws[i] = __ldg(w.p[model] + i);
   if (threadIdx.x < 32) bs[threadIdx.x] = __ldg(bias.p[model] + threadIdx.x);
   __syncthreads();
+#if !defined(OAT_STEM_1PX)
+  // One thread = two horizontally adjacent output pixels (every weight float4 feeds 8 FMAs;
+  // -DOAT_STEM_1PX selects the one-pixel form).
+  // Loads are unconditional on clamped coordinates and masked by a 0/1 factor.
+  const int64_t pair = (int64_t)blockIdx.x * STEM_THREADS + threadIdx.x;
+  if (pair >= (int64_t)B * 1250) return;
+  const int ow = 2 * (int)(pair % 25), oh = (int)((pair / 25) % 50);
+  const int64_t b = pair / 1250;
+  float acc0[32], acc1[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { acc0[i] = bs[i]; acc1[i] = bs[i]; }
+  for (int c = 0; c < C; ++c) {
+    const float* plane = vis + (b * C + c) * 10000;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = 2 * oh - 1 + kh;
+      const int ihc = min(max(ih, 0), 99);
+      const float rmask = (ih == ihc) ? 1.0f : 0.0f;
+      float v[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int iw = 2 * ow - 1 + j;
+        const int iwc = min(max(iw, 0), 99);
+        v[j] = __ldg(plane + ihc * 100 + iwc) * ((iw == iwc) ? rmask : 0.0f);
+      }
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((kh * 3 + kw) * C + c) * 32);
+        const float va = v[kw], vb = v[kw + 2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 wv = wr[j];
+          acc0[4 * j + 0] = fmaf(va, wv.x, acc0[4 * j + 0]);
+          acc0[4 * j + 1] = fmaf(va, wv.y, acc0[4 * j + 1]);
+          acc0[4 * j + 2] = fmaf(va, wv.z, acc0[4 * j + 2]);
+          acc0[4 * j + 3] = fmaf(va, wv.w, acc0[4 * j + 3]);
+          acc1[4 * j + 0] = fmaf(vb, wv.x, acc1[4 * j + 0]);
+          acc1[4 * j + 1] = fmaf(vb, wv.y, acc1[4 * j + 1]);
+          acc1[4 * j + 2] = fmaf(vb, wv.z, acc1[4 * j + 2]);
+          acc1[4 * j + 3] = fmaf(vb, wv.w, acc1[4 * j + 3]);
+        }
+      }
+    }
+  }
+  const int64_t pix = b * 2500 + (int64_t)oh * 50 + ow;
+  float4* dst = reinterpret_cast<float4*>(out + ((int64_t)model * B * 2500 + pix) * 32);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    dst[j] = make_float4(relu6f(acc0[4 * j]), relu6f(acc0[4 * j + 1]), relu6f(acc0[4 * j + 2]),
+                         relu6f(acc0[4 * j + 3]));
+    dst[8 + j] = make_float4(relu6f(acc1[4 * j]), relu6f(acc1[4 * j + 1]), relu6f(acc1[4 * j + 2]),
+                             relu6f(acc1[4 * j + 3]));
+  }
+}
+#else
   const int64_t pix = (int64_t)blockIdx.x * STEM_THREADS + threadIdx.x;
   if (pix >= (int64_t)B * 2500) return;
   const int ow = (int)(pix % 50), oh = (int)((pix / 50) % 50);
@@ -99,6 +154,7 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_kernel(
     dst[j] = make_float4(relu6f(acc[4 * j]), relu6f(acc[4 * j + 1]), relu6f(acc[4 * j + 2]),
                          relu6f(acc[4 * j + 3]));
 }
+#endif
 
 // ---------------------------------------------------------------------------
 // pointwise (1x1) convolution = GEMM  C[M,N] = act(A[M,K] W[K,N] + bias) (+ R).
@@ -336,6 +392,65 @@ __global__ void __launch_bounds__(OAT_DW_THREADS) dw_kernel(const __grid_constan
   }
 }
 
+#if !defined(OAT_DW_1ROW)
+// Stride 1: one thread = 4 channels x TWO output rows; the 4 input rows are loaded once per
+// column (4 loads for 2 outputs instead of 6).  -DOAT_DW_1ROW selects the one-row kernel.
+__global__ void __launch_bounds__(OAT_DW_THREADS) dw2_kernel(const __grid_constant__ PtrTable w,
+                                                            const __grid_constant__ PtrTable bias,
+                                                            const float* __restrict__ in,
+                                                            float* __restrict__ out, int B, int H,
+                                                            int C) {
+  const int model = blockIdx.y;
+  const int C4 = C >> 2;
+  const int HP = (H + 1) >> 1;  // row pairs
+  const int64_t total = (int64_t)B * HP * C4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  const int oh = 2 * (int)((idx / C4) % HP);
+  const int64_t b = idx / ((int64_t)C4 * HP);
+  const float* __restrict__ wm = w.p[model] + 4 * c4;
+  float4 k[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(wm + t * C));
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias.p[model] + 4 * c4));
+  const float* __restrict__ src = in + ((int64_t)model * B + b) * H * H * C + 4 * c4;
+  float* __restrict__ dst = out + (((int64_t)model * B + b) * H + oh) * H * C + 4 * c4;
+  const bool second = oh + 1 < H;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto ldcol = [&](int iw, float4 (&col)[4]) {
+    const bool cv = iw >= 0 && iw < H;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ih = oh - 1 + r;
+      col[r] = (cv && ih >= 0 && ih < H)
+                   ? __ldg(reinterpret_cast<const float4*>(src + ((int64_t)ih * H + iw) * C))
+                   : zero;
+    }
+  };
+  float4 L[4], M[4], R[4];
+  ldcol(-1, L);
+  ldcol(0, M);
+  for (int ow = 0; ow < H; ++ow) {
+    ldcol(ow + 1, R);
+    float4 a0 = bv, a1 = bv;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      a0 = fma4(L[r], k[3 * r + 0], a0); a0 = fma4(M[r], k[3 * r + 1], a0); a0 = fma4(R[r], k[3 * r + 2], a0);
+      a1 = fma4(L[r + 1], k[3 * r + 0], a1); a1 = fma4(M[r + 1], k[3 * r + 1], a1); a1 = fma4(R[r + 1], k[3 * r + 2], a1);
+    }
+    a0.x = relu6f(a0.x); a0.y = relu6f(a0.y); a0.z = relu6f(a0.z); a0.w = relu6f(a0.w);
+    *reinterpret_cast<float4*>(dst + (int64_t)ow * C) = a0;
+    if (second) {
+      a1.x = relu6f(a1.x); a1.y = relu6f(a1.y); a1.z = relu6f(a1.z); a1.w = relu6f(a1.w);
+      *reinterpret_cast<float4*>(dst + ((int64_t)H + ow) * C) = a1;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { L[r] = M[r]; M[r] = R[r]; }
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------
 // global average pool over P pixels: [E*B][P][C] -> [E*B][C].
 // ---------------------------------------------------------------------------
@@ -426,7 +541,11 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
   {
     PtrTable w = table([](const OatModel* m) { return m->stem.w; });
     PtrTable b = table([](const OatModel* m) { return m->stem.b; });
+#if !defined(OAT_STEM_1PX)
+    dim3 grid((unsigned)(((int64_t)B * 1250 + STEM_THREADS - 1) / STEM_THREADS), E);
+#else
     dim3 grid((unsigned)(((int64_t)B * 2500 + STEM_THREADS - 1) / STEM_THREADS), E);
+#endif
     stem_kernel<<<grid, STEM_THREADS, 0, stream>>>(w, b, visual, B, C, ens->bufA);
     OAT_LAUNCH_CHECK();
   }
@@ -457,9 +576,17 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       PtrTable b = table([bi](const OatModel* m) { return m->blocks[bi].dw.b; });
       const int64_t total = (int64_t)B * blk.hout * (blk.hid / 4);
       dim3 grid((unsigned)((total + OAT_DW_THREADS - 1) / OAT_DW_THREADS), E);
+#if !defined(OAT_DW_1ROW)
+      if (blk.stride == 1) {
+        const int64_t tot2 = (int64_t)B * ((blk.hout + 1) / 2) * (blk.hid / 4);
+        dim3 grid2((unsigned)((tot2 + OAT_DW_THREADS - 1) / OAT_DW_THREADS), E);
+        dw2_kernel<<<grid2, OAT_DW_THREADS, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hid);
+      } else
+#else
       if (blk.stride == 1)
         dw_kernel<1><<<grid, OAT_DW_THREADS, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid);
       else
+#endif
         dw_kernel<2><<<grid, OAT_DW_THREADS, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid);
       OAT_LAUNCH_CHECK();
     }
