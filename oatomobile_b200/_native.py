@@ -111,7 +111,7 @@ def set_default_pw_impl(impl: str) -> None:
 
 def set_flow_impl(impl: str) -> None:
   """"tcgen05" (default) or "simt": kernel family of the autoregressive flow."""
-  check(lib().oat_set_flow_impl({"simt": 0, "tcgen05": 1}[impl]))
+  check(lib().oat_set_flow_impl({"simt": 0, "tcgen05": 1, "tcgen05x2": 2}[impl]))
 
 
 def launch_count() -> int:

@@ -17,7 +17,10 @@ namespace oat {
 
 static thread_local std::string g_error;
 int64_t g_launch_count = 0;
-int g_flow_impl = 1;
+#ifndef OAT_FLOW_DEFAULT_IMPL
+#define OAT_FLOW_DEFAULT_IMPL 1
+#endif
+int g_flow_impl = OAT_FLOW_DEFAULT_IMPL;
 
 void set_error(const std::string& msg) { g_error = msg; }
 int fail(const std::string& msg) {
@@ -503,16 +506,24 @@ int oat_encode(OatEnsemble* ens, const float* visual, const float* scalars, int3
 static PtrTable one_model(const OatModel* m) {
   PtrTable t;
   for (int i = 0; i < kMaxModels; ++i) t.p[i] = nullptr;
-  t.p[0] = (g_flow_impl == 1 && m->flow_tc) ? m->flow_tc : m->flow;
+  t.p[0] = (g_flow_impl >= 1 && m->flow_tc) ? m->flow_tc : m->flow;
   return t;
 }
 
 static int dispatch_flow(const FlowLaunch& a, cudaStream_t stream) {
-  return (g_flow_impl == 1 && a.mode != 2) ? launch_flow_tc(a, stream) : launch_flow(a, stream);
+  // The tensor-core kernels keep the whole [rows, 2T] x/y tile in shared memory next to the
+  // 118 KB weight image and the state tile: two-tile form up to T = 20, one-tile form up to
+  // T = 40; longer horizons (CIL uses up to 40, anything beyond is exotic) take the SIMT kernel.
+  if (g_flow_impl >= 1 && a.mode != 2) {
+    if (g_flow_impl == 2 && a.T <= 20) return launch_flow_tc2(a, stream);
+    if (a.T <= 40) return launch_flow_tc(a, stream);
+  }
+  return launch_flow(a, stream);
 }
 
 int oat_set_flow_impl(int32_t impl) {
-  if (impl != 0 && impl != 1) return fail("oat_set_flow_impl: impl must be 0 (simt) or 1 (tcgen05)");
+  if (impl < 0 || impl > 2)
+    return fail("oat_set_flow_impl: impl must be 0 (simt), 1 (tcgen05) or 2 (tcgen05, two tiles/CTA)");
   g_flow_impl = impl;
   return 0;
 }
@@ -576,7 +587,7 @@ int oat_rip_sample_score(OatEnsemble* ens, int32_t proposal_idx, const float* z,
   // scores under every (other) local model (rip/agent.py:109-119)
   a.mode = 1; a.num_models = E;
   for (int i = 0; i < kMaxModels; ++i)
-    a.weights.p[i] = i < E ? (g_flow_impl == 1 ? ens->models[i]->flow_tc : ens->models[i]->flow) : nullptr;
+    a.weights.p[i] = i < E ? (g_flow_impl >= 1 ? ens->models[i]->flow_tc : ens->models[i]->flow) : nullptr;
   a.in = y; a.z = z; a.z_model_stride = (int64_t)B * kHidden;
   a.out = nullptr; a.q = q; a.out_model_stride = N; a.skip_model = proposal_idx;
   return dispatch_flow(a, (cudaStream_t)stream);

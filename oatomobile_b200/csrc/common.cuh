@@ -140,6 +140,7 @@ struct FlowLaunch {
 };
 int launch_flow(const FlowLaunch& a, cudaStream_t stream);
 int launch_flow_tc(const FlowLaunch& a, cudaStream_t stream);
+int launch_flow_tc2(const FlowLaunch& a, cudaStream_t stream);  // two tiles per CTA (flow_tc2.cu)
 
 struct PlanLaunch {
   PtrTable w;  // per-model planner images (kFlowPlanFloats)
@@ -166,7 +167,7 @@ int launch_lidar_bev(const float* points, int64_t n, int pixels_per_meter, int h
 int launch_goal_likelihood(const float* y_last, const float* goal, int B, int G, float epsilon,
                            float* rows, float* mean, cudaStream_t stream);  // weights = flow_tc images
 void pack_flow_tc_image(const float* flow_weights, float* image);
-extern int g_flow_impl;  // 1 = tcgen05 (default), 0 = FP32 SIMT
+extern int g_flow_impl;  // 0 = FP32 SIMT, 1 = tcgen05 one tile/CTA, 2 = tcgen05 two tiles/CTA
 
 int launch_aggregate(const float* q, int E, int B, int K, int algo, const float* y, int T,
                      float* s, int32_t* kstar, float* sbest, float* plan,

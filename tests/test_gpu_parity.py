@@ -12,13 +12,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(autouse=True, params=["tcgen05", "simt"])
+@pytest.fixture(autouse=True, params=["tcgen05", "simt", "tcgen05x2"])
 def kernel_family(request):
-  """Every parity test runs on both kernel families: the tcgen05/TMA 3xTF32 path
-  (default) and the FP32 SIMT path."""
+  """Every parity test runs on every kernel family: the tcgen05/TMA 3xTF32 path (default),
+  the FP32 SIMT path, and the tcgen05 flow with two row tiles per CTA."""
   from oatomobile_b200 import _native
   _native.set_flow_impl(request.param)
-  _native.set_default_pw_impl(request.param)
+  _native.set_default_pw_impl("simt" if request.param == "simt" else "tcgen05")
   yield request.param
   _native.set_flow_impl("tcgen05")
   _native.set_default_pw_impl("tcgen05")

@@ -30,6 +30,8 @@ def timeit(fn, n=10):
   e1.record(); torch.cuda.synchronize()
   return e0.elapsed_time(e1) / n
 
+if os.environ.get("OAT_FLOW_IMPL"):
+  _native.set_flow_impl(os.environ["OAT_FLOW_IMPL"])
 sc = RIPScorer(models, "WCM")
 z = sc.encode(**ctx)
 t_enc = timeit(lambda: sc.encode(**ctx))
@@ -38,5 +40,10 @@ _native.set_default_pw_impl("simt")
 sc2 = RIPScorer(models, "WCM")
 z_ref = sc2.encode(**ctx)
 rel = ((z - z_ref).abs() / torch.clamp(torch.maximum(z.abs(), z_ref.abs()), min=1.0)).max().item()
-print("VARIANT %s  encode %.3f ms  flow %.3f ms  z-vs-simt %.2e" %
-      (os.path.basename(os.environ.get("OAT_B200_LIB", "default")), t_enc, t_flow, rel))
+y1, q1 = ops.rip_sample_score(sc._ensemble(), z, x, goal, 1.0)
+_native.set_flow_impl("simt")
+y0, q0 = ops.rip_sample_score(sc._ensemble(), z, x, goal, 1.0)
+relq = ((q1 - q0).abs() / torch.clamp(torch.maximum(q1.abs(), q0.abs()), min=1.0)).max().item()
+print("VARIANT %s flow=%s  encode %.3f ms  flow %.3f ms  z-vs-simt %.2e  q-vs-simt %.2e" %
+      (os.path.basename(os.environ.get("OAT_B200_LIB", "default")),
+       os.environ.get("OAT_FLOW_IMPL", "default"), t_enc, t_flow, rel, relq))
