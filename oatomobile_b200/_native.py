@@ -91,6 +91,8 @@ def lib() -> ctypes.CDLL:
         fn.restype = c_int
     L.oat_plan_workspace_floats.restype = c_i64
     _lib = L
+    if os.environ.get("OAT_FLOW_IMPL"):  # A/B switch: simt | tcgen05 | tcgen05x2
+      L.oat_set_flow_impl({"simt": 0, "tcgen05": 1, "tcgen05x2": 2}[os.environ["OAT_FLOW_IMPL"]])
     return L
 
 

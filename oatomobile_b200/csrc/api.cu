@@ -18,7 +18,7 @@ namespace oat {
 static thread_local std::string g_error;
 int64_t g_launch_count = 0;
 #ifndef OAT_FLOW_DEFAULT_IMPL
-#define OAT_FLOW_DEFAULT_IMPL 1
+#define OAT_FLOW_DEFAULT_IMPL 2
 #endif
 int g_flow_impl = OAT_FLOW_DEFAULT_IMPL;
 
@@ -512,10 +512,10 @@ static PtrTable one_model(const OatModel* m) {
 
 static int dispatch_flow(const FlowLaunch& a, cudaStream_t stream) {
   // The tensor-core kernels keep the whole [rows, 2T] x/y tile in shared memory next to the
-  // 118 KB weight image and the state tile: two-tile form up to T = 20, one-tile form up to
+  // 118 KB weight image and the state tile: two-tile form up to T = 16, one-tile form up to
   // T = 40; longer horizons (CIL uses up to 40, anything beyond is exotic) take the SIMT kernel.
   if (g_flow_impl >= 1 && a.mode != 2) {
-    if (g_flow_impl == 2 && a.T <= 20) return launch_flow_tc2(a, stream);
+    if (g_flow_impl == 2 && a.T <= 16) return launch_flow_tc2(a, stream);
     if (a.T <= 40) return launch_flow_tc(a, stream);
   }
   return launch_flow(a, stream);

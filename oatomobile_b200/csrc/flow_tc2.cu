@@ -55,7 +55,8 @@ static_assert(kImageBytes == kFlowTcFloats * 4, "flow TC image size mismatch");
 constexpr int OFF_HHI = ((kImageBytes + 1023) / 1024) * 1024;
 constexpr int OFF_HLO = OFF_HHI + 2 * kH_BYTES;
 constexpr int OFF_YPREV = OFF_HLO + 2 * kH_BYTES;    // [128][2]
-constexpr int OFF_IO = OFF_YPREV + 2 * TR * 2 * 4;   // [256][2T]
+constexpr int OFF_OHALF = OFF_YPREV + 2 * TR * 2 * 4;  // [256][4] partial head outputs of half 1
+constexpr int OFF_IO = OFF_OHALF + 2 * TR * 4 * 4;    // [256][2T]
 
 struct FlowTc2Args {
   PtrTable images;  // per-model pre-swizzled TC weight image
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc2_kernel(const __grid_cons
     const float* B2 = reinterpret_cast<const float*>(sptr + OFF_B2);
     float* yprev = reinterpret_cast<float*>(sptr + OFF_YPREV);
     float* io = reinterpret_cast<float*>(sptr + OFF_IO);
+    float* ohalf = reinterpret_cast<float*>(sptr + OFF_OHALF);
     const uint32_t hhi_row = sbase + OFF_HHI + hf * kH_BYTES + hrow * 128;
     const uint32_t hlo_row = sbase + OFF_HLO + hf * kH_BYTES + hrow * 128;
     int pub_event = 0;
@@ -371,25 +373,32 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc2_kernel(const __grid_cons
       }
       publish_h(h);  // -> head MMA of step t and recurrent MMA of step t+1
 
-      // ---- head + affine flow update: the 4 warps of half 0 own one row each ------------
+      // ---- head layer 1: both halves reduce 16 of the 32 head units each; half 1 hands its
+      // partial sums over through shared memory, half 0 finishes the row -------------------
+      mbar_wait(bar_d2, (uint32_t)(t & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+      {
+        uint32_t d[16];
+        tmem_ld16_nowait(trow + 192 + hf * 16, d);
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int j = hf * 16 + u;
+          const float av = fmaxf(__uint_as_float(d[u]) + B1[j], 0.0f);
+          o0 = fmaf(av, W2[j], o0);
+          o1 = fmaf(av, W2[32 + j], o1);
+          o2 = fmaf(av, W2[64 + j], o2);
+          o3 = fmaf(av, W2[96 + j], o3);
+        }
+      }
+      if (hf == 1) *reinterpret_cast<float4*>(ohalf + 4 * row) = make_float4(o0, o1, o2, o3);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + tl) : "memory");  // partial sums visible
       if (hf == 0) {
-        mbar_wait(bar_d2, (uint32_t)(t & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float o0 = B2[0], o1 = B2[1], o2 = B2[2], o3 = B2[3];
-#pragma unroll
-        for (int half16 = 0; half16 < 2; ++half16) {
-          uint32_t d[16];
-          tmem_ld16_nowait(trow + 192 + half16 * 16, d);
-          tmem_wait_ld();
-#pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int j = half16 * 16 + u;
-            const float av = fmaxf(__uint_as_float(d[u]) + B1[j], 0.0f);
-            o0 = fmaf(av, W2[j], o0);
-            o1 = fmaf(av, W2[32 + j], o1);
-            o2 = fmaf(av, W2[64 + j], o2);
-            o3 = fmaf(av, W2[96 + j], o3);
-          }
+        {
+          const float4 p = *reinterpret_cast<const float4*>(ohalf + 4 * row);
+          o0 += p.x + B2[0]; o1 += p.y + B2[1]; o2 += p.z + B2[2]; o3 += p.w + B2[3];
         }
         const float mu0 = yp.x + o0, mu1 = yp.y + o1;
         const float s0 = softplus_ref(o2) + 1e-3f, s1 = softplus_ref(o3) + 1e-3f;

@@ -20,7 +20,7 @@ def kernel_family(request):
   _native.set_flow_impl(request.param)
   _native.set_default_pw_impl("simt" if request.param == "simt" else "tcgen05")
   yield request.param
-  _native.set_flow_impl("tcgen05")
+  _native.set_flow_impl("tcgen05x2")  # library default
   _native.set_default_pw_impl("tcgen05")
 
 
