@@ -119,7 +119,19 @@ class RIPScorer:
     self._mark("step_begin")
     if "lidar" in context:
       context = dict(context)
-      context["visual_features"] = ops.transform_visual(context.pop("lidar"))
+      lidar = context.pop("lidar")
+      B = lidar.shape[0]
+      if self._world > 1 and B % self._world == 0:
+        # every rank needs every scene's features: resize 1/R of the scenes here and
+        # all-gather the (4x smaller) result over NVLink instead of R redundant resizes
+        import torch.distributed as dist
+        lo = self._rank * (B // self._world)
+        part = ops.transform_visual(lidar[lo:lo + B // self._world])
+        vis = torch.empty((B,) + tuple(part.shape[1:]), device=part.device, dtype=part.dtype)
+        dist.all_gather_into_tensor(vis, part, group=self._group)
+        context["visual_features"] = vis
+      else:
+        context["visual_features"] = ops.transform_visual(lidar)
     self._mark("encode_begin")
     z = self.encode(**context)
     self._mark("encode_end")
@@ -152,8 +164,13 @@ class HostRIPPipeline:
     self.d2h_bytes = 0
 
   def _upload(self, host, lo, hi, slot):
-    """Async H2D of scenes [lo,hi) into buffer `slot` on the copy stream."""
+    """Async H2D of scenes [lo,hi) into buffer `slot` on the copy stream.
+
+    When the ensemble is sharded over R ranks every rank needs every scene, but each rank
+    pulls only its 1/R slice over PCIe; `_assemble` then all-gathers the slices over NVLink."""
     h2d = 0
+    R, r = self._scorer._world, self._scorer._rank
+    shard = R > 1 and (hi - lo) % R == 0
     with torch.cuda.stream(self._copy_stream):
       self._copy_stream.wait_event(self._consumed[slot])  # previous user of the slot is done
       for k in self.INPUT_KEYS:
@@ -162,10 +179,27 @@ class HostRIPPipeline:
         if buf is None or buf.shape != src.shape:
           buf = torch.empty(src.shape, dtype=torch.float32, device=self._device)
           self._dev[slot][k] = buf
-        buf.copy_(src, non_blocking=True)
-        h2d += src.numel() * 4
+        if shard:
+          n = (hi - lo) // R
+          buf[r * n:(r + 1) * n].copy_(src[r * n:(r + 1) * n], non_blocking=True)
+          h2d += src[r * n:(r + 1) * n].numel() * 4
+        else:
+          buf.copy_(src, non_blocking=True)
+          h2d += src.numel() * 4
       self._uploaded[slot].record(self._copy_stream)
+    self._sharded = shard
     return h2d
+
+  def _assemble(self, slot):
+    """Sharded uploads: all-gather every input in place (compute stream, NCCL/NVLink)."""
+    if not getattr(self, "_sharded", False):
+      return
+    import torch.distributed as dist
+    R, r = self._scorer._world, self._scorer._rank
+    for k in self.INPUT_KEYS:
+      buf = self._dev[slot][k]
+      n = buf.shape[0] // R
+      dist.all_gather_into_tensor(buf, buf[r * n:(r + 1) * n].clone(), group=self._scorer._group)
 
   def __call__(self, host: Dict[str, torch.Tensor], epsilon: float = 1.0):
     B = host["lidar"].shape[0]
@@ -187,6 +221,7 @@ class HostRIPPipeline:
       if i + 1 < n:  # prefetch the next slice while this one is scored
         h2d += self._upload(host, bounds[i + 1][0], bounds[i + 1][1], slot ^ 1)
       compute.wait_event(self._uploaded[slot])
+      self._assemble(slot)
       d = dict(self._dev[slot])
       x, goal = d.pop("x"), d.pop("goal")
       out = self._scorer(x=x, goal=goal, epsilon=epsilon, **d)
@@ -213,6 +248,7 @@ class HostRIPPipeline:
       """upload + score + async D2H of one batch; returns (results, done event)."""
       h2d = self._upload(batch, 0, batch["lidar"].shape[0], slot)
       compute.wait_event(self._uploaded[slot])
+      self._assemble(slot)
       d = dict(self._dev[slot])
       x, goal = d.pop("x"), d.pop("goal")
       out = self._scorer(x=x, goal=goal, epsilon=epsilon, **d)

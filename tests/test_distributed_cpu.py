@@ -94,6 +94,7 @@ def _install_cpu_ops():
     return ks.int(), s[idx, ks], y[idx, ks], (s if want_s else None)
 
   _native.EnsembleHandle = FakeEnsemble
+  ops.transform_visual = R.transform_visual
   ops.encode, ops.flow_forward = encode, flow_forward
   ops.rip_sample_score, ops.rip_aggregate = rip_sample_score, rip_aggregate
 
@@ -116,8 +117,11 @@ def _worker(rank, world, port, algo, out_path):
   scorer = RIPScorer(mine, algo, group=group,
                      proposal_model=None if rank == 0 else _FakeModel(sds[0]))
   with torch.no_grad():
-    vis = R.transform_visual(inp["lidar"])
-    out = scorer(x=inp["x"], goal=inp["goal"], epsilon=1.0, want_s=True, visual_features=vis,
+    # raw grids: exercises the sharded resize + all-gather of visual features too (B=3 is not
+    # divisible by 2 ranks for "MA" -> replicated resize; B=4 for "WCM" -> sharded)
+    if algo == "WCM":
+      inp = synthetic_inputs(4, C, K, T, seed=4)
+    out = scorer(x=inp["x"], goal=inp["goal"], epsilon=1.0, want_s=True, lidar=inp["lidar"],
                  velocity=inp["velocity"], is_at_traffic_light=inp["is_at_traffic_light"],
                  traffic_light_state=inp["traffic_light_state"])
     ref = R.rip_score_from_inputs(sds, inp["lidar"], inp["velocity"], inp["is_at_traffic_light"],
@@ -186,7 +190,7 @@ def test_sharded_scorer_world2_matches_single_process(tmp_path, algo):
   for r in range(world):
     res = torch.load(out_path % r)
     assert res["ok"], "rank %d diverged from the single-process oracle" % r
-    assert res["q_shape"] == (E, B, K)
+    assert res["q_shape"] == (E, 4 if algo == "WCM" else B, K)
 
 
 def test_non_zero_rank_needs_proposal_model():
