@@ -170,6 +170,63 @@ OAT_API int oat_debug_tc_gemm(const float* A, const float* W, const float* bias,
                       float* C, int32_t M, int32_t K, int32_t N, int32_t E, int32_t relu6,
                       void* stream);
 
+/* ---- training step ----------------------------------------
+ * A named DEVICE tensor of a model that is being trained: `param` points at the
+ * storage of the reference `state_dict` entry (reference layout, float32), `grad`
+ * at the storage of its gradient (NULL for BatchNorm running statistics).       */
+typedef struct OatTrainTensor {
+  const char* name;
+  void* param;
+  void* grad;
+  int32_t ndim;
+  int64_t shape[4];
+} OatTrainTensor;
+
+typedef struct OatTrainer OatTrainer;
+
+/* Binds the trainer to the caller-owned parameter / gradient storage of one
+ * `ImitativeModel` (kind OAT_KIND_DIM) or `BehaviouralModel` (OAT_KIND_CIL).  If all
+ * gradients live in one flat buffer pass it as (grad_flat, grad_flat_floats) so it is
+ * cleared with one memset per step; otherwise pass NULL/0.                       */
+OAT_API int oat_trainer_create(const OatTrainTensor* tensors, int32_t num_tensors, int32_t kind,
+                       int32_t device, float* grad_flat, int64_t grad_flat_floats,
+                       OatTrainer** out);
+OAT_API int oat_trainer_destroy(OatTrainer* trainer);
+
+/* Forward in `model.train()` mode + loss + backward of the reference `train_step`
+ * up to (not including) `optimizer.step()`:
+ *   DIM (dim/train.py:190-203): z = _params(batch); loss = -mean(log_prob - logabsdet)
+ *       of `target` (the perturbed `player_future[..., :2]`) under `_decoder._inverse`;
+ *   CIL (cil/train.py:176-184): loss = mean_b sum_{t,d} |forward(batch) - target|.
+ * visual [B,C,100,100] (post-`transform`), scalars [B,5|6] = velocity(3) |
+ * is_at_traffic_light | traffic_light_state (| mode), target [B,T,2], dropout_mask
+ * [B,1280] = Bernoulli(0.8)/0.8 for the classifier's Dropout(0.2) or NULL (p = 0).
+ * BatchNorm layers use batch statistics and update running_mean / running_var
+ * (momentum 0.1) in place.  Every gradient is overwritten.  Outputs: loss [1];
+ * optional z [B,64] and (CIL) pred [B,T,2].                                       */
+OAT_API int oat_train_forward_backward(OatTrainer* trainer, const float* visual, const float* scalars,
+                               const float* target, const float* dropout_mask, int32_t B,
+                               int32_t T, float* loss, float* z, float* pred, void* stream);
+
+/* Debug/test access to the post-activation outputs of the last
+ * oat_train_forward_backward call: index 0..51 = the 52 conv+BN units in execution order,
+ * NHWC rows [B*h*h][channels]; 52..54 = the three merger layers [B][64].  Always reports
+ * the shape; when `out` is not NULL the activation is copied (device to device, on
+ * `stream`) into it.  The gradient tests use this to evaluate the float64 oracle on the
+ * same ReLU/ReLU6 branch the kernels took.                                          */
+OAT_API int oat_trainer_activation(const OatTrainer* trainer, int32_t index, float* out,
+                           int64_t* rows, int32_t* channels, void* stream);
+
+/* `torch.optim.Adam.step()` (+ L2 `weight_decay`) over one flat parameter range, with
+ * gradients first multiplied by `grad_scale` (1/world_size after an all-reduce SUM) and
+ * optionally clipped to global norm `clip_norm` (> 0; `clip_grad_norm_`,
+ * dim/train.py:207-208).  `step` is the 1-based step count; `norm_ws` is one double of
+ * device scratch (needed only when clipping).                                     */
+OAT_API int oat_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  int32_t step, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, float grad_scale, float clip_norm, double* norm_ws,
+                  void* stream);
+
 /* Number of kernel launches issued by this library since load (bench.py's
  * `gpu_launches`). */
 OAT_API int64_t oat_launch_count(void);

@@ -24,7 +24,8 @@ SYMBOLS = (
     "oat_flow_inverse", "oat_rip_sample_score", "oat_rip_aggregate", "oat_cil_rollout",
     "oat_launch_count", "oat_ensemble_set_pw_impl", "oat_debug_tc_gemm",
     "oat_set_flow_impl", "oat_plan", "oat_plan_workspace_floats", "oat_goal_likelihood",
-    "oat_transform_visual_hwc", "oat_lidar_bev",
+    "oat_transform_visual_hwc", "oat_lidar_bev", "oat_trainer_create", "oat_trainer_destroy",
+    "oat_train_forward_backward", "oat_adam_step", "oat_trainer_activation",
 )
 
 
@@ -34,6 +35,11 @@ class NativeLibraryError(RuntimeError):
 
 class OatTensor(ctypes.Structure):
   _fields_ = [("name", ctypes.c_char_p), ("h_data", ctypes.c_void_p),
+              ("ndim", ctypes.c_int32), ("shape", ctypes.c_int64 * 4)]
+
+
+class OatTrainTensor(ctypes.Structure):
+  _fields_ = [("name", ctypes.c_char_p), ("param", ctypes.c_void_p), ("grad", ctypes.c_void_p),
               ("ndim", ctypes.c_int32), ("shape", ctypes.c_int64 * 4)]
 
 
@@ -84,6 +90,14 @@ def lib() -> ctypes.CDLL:
     L.oat_lidar_bev.argtypes = [vp, c_i64, c_i32, c_i32, c_i32, vp, vp, vp]
     L.oat_goal_likelihood.argtypes = [vp, vp, c_i32, c_i32, c_f, vp, vp, vp]
     L.oat_debug_tc_gemm.argtypes = [vp, vp, vp, vp, vp, c_i32, c_i32, c_i32, c_i32, c_i32, vp]
+    L.oat_trainer_create.argtypes = [ctypes.POINTER(OatTrainTensor), c_i32, c_i32, c_i32, vp, c_i64,
+                                     ctypes.POINTER(vp)]
+    L.oat_trainer_destroy.argtypes = [vp]
+    L.oat_train_forward_backward.argtypes = [vp, vp, vp, vp, vp, c_i32, c_i32, vp, vp, vp, vp]
+    L.oat_trainer_activation.argtypes = [vp, c_i32, vp, ctypes.POINTER(c_i64),
+                                         ctypes.POINTER(c_i32), vp]
+    L.oat_adam_step.argtypes = [vp, vp, vp, vp, c_i64, c_i32, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
+                                vp, vp]
     for name in SYMBOLS:
       fn = getattr(L, name, None)
       if fn is not None and name not in ("oat_last_error", "oat_launch_count",

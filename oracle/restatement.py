@@ -84,24 +84,43 @@ def transform_visual(lidar: Tensor) -> Tensor:
 # ----------------------------------------------------------------------------
 # a2. MobileNetV2 encoder (perception.py:25-55 + torchvision mobilenet_v2, eval)
 # ----------------------------------------------------------------------------
-def _bn(x: Tensor, sd: StateDict, p: str) -> Tensor:
-  """Eval-mode BatchNorm2d: (x-mean)/sqrt(var+eps)*gamma+beta."""
-  mean = sd[p + ".running_mean"].view(1, -1, 1, 1)
-  var = sd[p + ".running_var"].view(1, -1, 1, 1)
+def _bn(x: Tensor, sd: StateDict, p: str, train: Optional[dict] = None) -> Tensor:
+  """BatchNorm2d.  Eval mode (train is None): (x-mean)/sqrt(var+eps)*gamma+beta with the
+  running statistics.  Training mode (`model.train()`, dim/train.py:223): batch mean and
+  biased batch variance normalise; the updated running estimates (momentum 0.1, unbiased
+  variance) are recorded in `train["buffers"]`."""
   g = sd[p + ".weight"].view(1, -1, 1, 1)
   b = sd[p + ".bias"].view(1, -1, 1, 1)
-  return (x - mean) / torch.sqrt(var + BN_EPS) * g + b
+  if train is None:
+    mean = sd[p + ".running_mean"].view(1, -1, 1, 1)
+    var = sd[p + ".running_var"].view(1, -1, 1, 1)
+    return (x - mean) / torch.sqrt(var + BN_EPS) * g + b
+  train["unit"] = train.get("unit", 0) + 1  # conv+BN units in execution order, 1-based
+  n = x.numel() // x.shape[1]
+  mean = x.mean(dim=(0, 2, 3))
+  var = ((x - mean.view(1, -1, 1, 1))**2).mean(dim=(0, 2, 3))
+  with torch.no_grad():
+    train["buffers"][p + ".running_mean"] = 0.9 * sd[p + ".running_mean"] + 0.1 * mean
+    train["buffers"][p + ".running_var"] = 0.9 * sd[p + ".running_var"] + 0.1 * var * (n / max(n - 1, 1))
+  return (x - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + BN_EPS) * g + b
 
 
-def _relu6(x: Tensor) -> Tensor:
-  return x.clamp(min=0.0, max=6.0)
+def _relu6(x: Tensor, train: Optional[dict] = None) -> Tensor:
+  """ReLU6.  With `train["branch"]` (gradient checks only) the piecewise-linear branch is
+  not chosen by x but prescribed: branch[unit] = (pass-through mask, saturated-at-6 mask),
+  so that the float64 oracle differentiates the same linear piece a float32 implementation
+  took when a pre-activation sits within rounding distance of 0 or 6."""
+  if train is None or train.get("branch") is None:
+    return x.clamp(min=0.0, max=6.0)
+  passthrough, saturated = train["branch"][train["unit"] - 1]
+  return x * passthrough.to(x.dtype) + 6.0 * saturated.to(x.dtype)
 
 
-def _conv_bn_relu6(x, sd, p, stride, groups):
+def _conv_bn_relu6(x, sd, p, stride, groups, train=None):
   w = sd[p + ".0.weight"]
   pad = (w.shape[-1] - 1) // 2
   x = F.conv2d(x, w, None, stride=stride, padding=pad, groups=groups)
-  return _relu6(_bn(x, sd, p + ".1"))
+  return _relu6(_bn(x, sd, p + ".1", train), train)
 
 
 # (expand t, out c, repeats n, first stride s) — Sandler et al. 2018, table 2.
@@ -120,44 +139,58 @@ def mbv2_block_table():
   return table
 
 
-def mobilenet_v2_encode(sd: StateDict, x: Tensor, prefix: str = "_encoder._model.") -> Tensor:
-  """perception.py:53-55 → torchvision MobileNetV2.forward, eval mode (no dropout).
+def mobilenet_v2_encode(sd: StateDict, x: Tensor, prefix: str = "_encoder._model.",
+                        train: Optional[dict] = None) -> Tensor:
+  """perception.py:53-55 → torchvision MobileNetV2.forward.  Eval mode (no dropout) by
+  default; with `train` (a dict holding "buffers" and optionally "dropout_mask" [B,1280],
+  already scaled by 1/(1-p)) the BatchNorms use batch statistics and the classifier's
+  Dropout(0.2) multiplies the pooled features by the given mask.
 
   x: [B,C,100,100] → [B,128].
   """
   f = prefix + "features."
-  x = _conv_bn_relu6(x, sd, f + "0", stride=2, groups=1)
+  x = _conv_bn_relu6(x, sd, f + "0", stride=2, groups=1, train=train)
   for idx, cin, hid, cout, stride, res in mbv2_block_table():
     p = f + "%d.conv" % idx
     h = x
     if hid != cin:  # expand 1x1
-      h = _conv_bn_relu6(h, sd, p + ".0", stride=1, groups=1)
+      h = _conv_bn_relu6(h, sd, p + ".0", stride=1, groups=1, train=train)
       dw, pj, pjbn = p + ".1", p + ".2", p + ".3"
     else:  # t == 1: no expand conv
       dw, pj, pjbn = p + ".0", p + ".1", p + ".2"
-    h = _conv_bn_relu6(h, sd, dw, stride=stride, groups=hid)
-    h = _bn(F.conv2d(h, sd[pj + ".weight"], None), sd, pjbn)  # linear bottleneck
+    h = _conv_bn_relu6(h, sd, dw, stride=stride, groups=hid, train=train)
+    h = _bn(F.conv2d(h, sd[pj + ".weight"], None), sd, pjbn, train)  # linear bottleneck
     x = x + h if res else h
-  x = _conv_bn_relu6(x, sd, f + "18", stride=1, groups=1)
+  x = _conv_bn_relu6(x, sd, f + "18", stride=1, groups=1, train=train)
   x = x.mean(dim=(2, 3))  # adaptive_avg_pool2d(1) + flatten
+  if train is not None and train.get("dropout_mask") is not None:
+    x = x * train["dropout_mask"]
   return F.linear(x, sd[prefix + "classifier.1.weight"], sd[prefix + "classifier.1.bias"])
 
 
 # ----------------------------------------------------------------------------
 # a3/a4. merger MLP and _params (mlp.py:49-68, dim/model.py:173-219)
 # ----------------------------------------------------------------------------
-def mlp3_relu(sd: StateDict, u: Tensor, prefix: str = "_merger._model.") -> Tensor:
-  """MLP(.., [64,64,64], activate_final=True): Linear-ReLU x3 (mlp.py:49-66)."""
-  for i in (0, 2, 4):
-    u = F.relu(F.linear(u, sd[prefix + "%d.weight" % i], sd[prefix + "%d.bias" % i]))
+def mlp3_relu(sd: StateDict, u: Tensor, prefix: str = "_merger._model.",
+              train: Optional[dict] = None) -> Tensor:
+  """MLP(.., [64,64,64], activate_final=True): Linear-ReLU x3 (mlp.py:49-66).  A
+  prescribed branch (see `_relu6`) is read from train["branch"][52 + layer]."""
+  for j, i in enumerate((0, 2, 4)):
+    u = F.linear(u, sd[prefix + "%d.weight" % i], sd[prefix + "%d.bias" % i])
+    if train is not None and train.get("branch") is not None:
+      u = u * train["branch"][52 + j][0].to(u.dtype)
+    else:
+      u = F.relu(u)
   return u
 
 
 def imitative_params(sd: StateDict, visual_features: Tensor, velocity: Tensor,
-                     is_at_traffic_light: Tensor, traffic_light_state: Tensor) -> Tensor:
+                     is_at_traffic_light: Tensor, traffic_light_state: Tensor,
+                     train: Optional[dict] = None) -> Tensor:
   """dim/model.py:203-217 — z = merger(cat[encoder(v), vel, tl, tls]); [B,64]."""
-  e = mobilenet_v2_encode(sd, visual_features)
-  return mlp3_relu(sd, torch.cat([e, velocity, is_at_traffic_light, traffic_light_state], -1))
+  e = mobilenet_v2_encode(sd, visual_features, train=train)
+  return mlp3_relu(sd, torch.cat([e, velocity, is_at_traffic_light, traffic_light_state], -1),
+                   train=train)
 
 
 # ----------------------------------------------------------------------------
@@ -385,10 +418,11 @@ def rip_plan(sds, zs, T, goal, num_steps=10, lr=1e-1, epsilon=1.0, algorithm="WC
 # a13. BehaviouralModel.forward (cil/model.py:68-127)
 # ----------------------------------------------------------------------------
 def behavioural_forward(sd: StateDict, T: int, visual_features, velocity,
-                        is_at_traffic_light, traffic_light_state, mode) -> Tensor:
+                        is_at_traffic_light, traffic_light_state, mode, train=None) -> Tensor:
   """cil/model.py:88-127 — encoder → merger(134) → T x {GRUCell; x += Linear(h)}."""
-  e = mobilenet_v2_encode(sd, visual_features)
-  h = mlp3_relu(sd, torch.cat([e, velocity, is_at_traffic_light, traffic_light_state, mode], -1))
+  e = mobilenet_v2_encode(sd, visual_features, train=train)
+  h = mlp3_relu(sd, torch.cat([e, velocity, is_at_traffic_light, traffic_light_state, mode], -1),
+                train=train)
   x = torch.zeros(h.shape[0], 2, dtype=h.dtype)
   ys = []
   for _ in range(T):
@@ -397,6 +431,70 @@ def behavioural_forward(sd: StateDict, T: int, visual_features, velocity,
     x = F.linear(h, sd["_output.weight"], sd["_output.bias"]) + x
     ys.append(x)
   return torch.stack(ys, dim=1)
+
+
+# ----------------------------------------------------------------------------
+# a14. training steps (dim/train.py:175-213, cil/train.py:168-190)
+# ----------------------------------------------------------------------------
+def _leaf_state_dict(sd: StateDict):
+  """Floating-point entries as autograd leaves (buffers stay plain tensors)."""
+  out = {}
+  for k, v in sd.items():
+    if not v.is_floating_point():
+      out[k] = v
+    elif "running_" in k:
+      out[k] = v.detach().clone()
+    else:
+      out[k] = v.detach().clone().requires_grad_(True)
+  return out
+
+
+def train_forward_backward(sd: StateDict, kind: str, visual_features, scalars: Tensor,
+                           target: Tensor, dropout_mask: Optional[Tensor] = None,
+                           branch: Optional[dict] = None):
+  """`train_step` up to (not including) `optimizer.step()`, in `model.train()` mode.
+
+  kind "dim" (dim/train.py:190-203): z = _params(batch); loss = -mean(log_prob - logabsdet)
+  of `target` (the perturbed player_future[..., :2]) under `_decoder._inverse`.
+  kind "cil" (cil/train.py:176-184): loss = mean_b sum_{t,d} |forward(batch) - target|.
+  scalars = [velocity(3) | is_at_traffic_light | traffic_light_state (| mode)].
+  `branch` (gradient checks): {unit: (pass-through mask, saturated mask)} prescribing the
+  ReLU6 / ReLU linear piece per activation — units 0..51 NCHW masks, 52..54 the merger.
+  Returns (loss, grads {name: tensor}, new BatchNorm buffers {name: tensor}, z-or-pred)."""
+  leaves = _leaf_state_dict(sd)
+  train = {"buffers": {}, "dropout_mask": dropout_mask, "branch": branch}
+  vel, tl, tls = scalars[:, 0:3], scalars[:, 3:4], scalars[:, 4:5]
+  if kind == "dim":
+    z = imitative_params(leaves, visual_features, vel, tl, tls, train=train)
+    _, log_prob, logabsdet = flow_inverse(leaves, target, z)
+    loss = -torch.mean(log_prob - logabsdet, dim=0)
+    aux = z.detach()
+  else:
+    pred = behavioural_forward(leaves, target.shape[1], visual_features, vel, tl, tls,
+                               scalars[:, 5:6], train=train)
+    loss = torch.mean(torch.sum(torch.abs(pred - target), dim=[-2, -1]), dim=0)
+    aux = pred.detach()
+  names = [k for k, v in leaves.items() if v.is_floating_point() and v.requires_grad]
+  grads = torch.autograd.grad(loss, [leaves[k] for k in names])
+  return loss.detach(), dict(zip(names, grads)), train["buffers"], aux
+
+
+def adam_update(param, grad, exp_avg, exp_avg_sq, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                weight_decay=0.0):
+  """torch.optim.Adam single-tensor update (dim/train.py:115-119), returns the new
+  (param, exp_avg, exp_avg_sq)."""
+  if weight_decay != 0.0:
+    grad = grad + weight_decay * param
+  exp_avg = betas[0] * exp_avg + (1 - betas[0]) * grad
+  exp_avg_sq = betas[1] * exp_avg_sq + (1 - betas[1]) * grad * grad
+  denom = exp_avg_sq.sqrt() / math.sqrt(1 - betas[1]**step) + eps
+  return param - (lr / (1 - betas[0]**step)) * exp_avg / denom, exp_avg, exp_avg_sq
+
+
+def clip_coefficient(grads, max_norm: float) -> float:
+  """torch.nn.utils.clip_grad_norm_ (dim/train.py:207-208): min(1, max_norm/(||g||+1e-6))."""
+  total = math.sqrt(sum(float((g.double()**2).sum()) for g in grads))
+  return min(1.0, max_norm / (total + 1e-6))
 
 
 # ----------------------------------------------------------------------------

@@ -61,3 +61,50 @@ def observation(inp, b):
       "traffic_light_state": int(inp["traffic_light_state"][b, 0]),
       "goal": goal3.astype(np.float32),
   }
+
+
+# ---- training-step fixtures (tests/golden/make_golden_train.py uses the same functions) ----
+TRAIN_CONFIGS = {
+    "train_dim_T4_C2": dict(kind="dim", T=4, C=2, B=4, wseed=400, iseed=21, dropout_seed=None),
+    "train_cil_T4_C2": dict(kind="cil", T=4, C=2, B=4, wseed=500, iseed=22, dropout_seed=None),
+    "train_dim_T4_C2_dropout": dict(kind="dim", T=4, C=2, B=4, wseed=400, iseed=21, dropout_seed=77),
+}
+
+
+def train_inputs(cfg):
+  """Seeded batch: post-`transform` visual features [B,C,100,100], the vector inputs
+  [B,5|6] (velocity | is_at_traffic_light | traffic_light_state (| mode)), targets [B,T,2]."""
+  from oracle import restatement as R
+  B, C, T = cfg["B"], cfg["C"], cfg["T"]
+  inp = synthetic_inputs(B, C, 1, T, seed=cfg["iseed"])
+  g = torch.Generator().manual_seed(cfg["iseed"] + 1000)
+  target = torch.cumsum(torch.rand(B, T, 2, generator=g) * 2.0, dim=1)
+  mode = torch.randint(0, 4, (B, 1), generator=g).float()
+  visual = R.transform_visual(inp["lidar"]).contiguous()
+  cols = [inp["velocity"], inp["is_at_traffic_light"], inp["traffic_light_state"]]
+  if cfg["kind"] == "cil":
+    cols.append(mode)
+  return visual, torch.cat(cols, dim=1).contiguous(), target
+
+
+def dropout_mask(cfg):
+  """The mask nn.Dropout(0.2) draws as the first RNG consumer after manual_seed (CPU
+  generator), already scaled by 1/(1-p); None when the config disables dropout."""
+  if cfg["dropout_seed"] is None:
+    return None
+  torch.manual_seed(cfg["dropout_seed"])
+  return torch.nn.functional.dropout(torch.ones(cfg["B"], 1280), p=0.2, training=True)
+
+
+def grad_errors(grads, reference64):
+  """Per-tensor max |g - g64| relative to the tensor's largest |g64| entry; tensors whose
+  true gradient vanishes (BatchNorm biases in front of another BatchNorm) are compared in
+  absolute terms against the largest gradient entry of the whole model."""
+  top = max(float(v.abs().max()) for v in reference64.values())
+  out = {}
+  for k, g64 in reference64.items():
+    scale = float(g64.abs().max())
+    if scale < 1e-6 * top:
+      scale = top
+    out[k] = float((grads[k].detach().double().cpu() - g64).abs().max()) / scale
+  return out

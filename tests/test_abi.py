@@ -116,3 +116,12 @@ def test_checkpoint_interchange_with_reference(tmp_path):
     ref.load_state_dict(torch.load(path), strict=True)          # ours -> reference
     torch.save(ref.state_dict(), str(tmp_path / "ref.pt"))
     other.load_state_dict(torch.load(str(tmp_path / "ref.pt")), strict=True)  # reference -> ours
+
+
+def test_trainer_rejects_cpu_models():
+  """The training step has no CPU implementation either."""
+  import oatomobile_b200 as ob
+  from oatomobile_b200._native import NativeLibraryError
+  from oatomobile_b200.train import Trainer
+  with pytest.raises(NativeLibraryError):
+    Trainer(ob.ImitativeModel(output_shape=(4, 2)))

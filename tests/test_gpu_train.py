@@ -1,0 +1,162 @@
+"""Training step on the GPU against the oracle and the goldens.
+
+Parity bars: loss 2e-6 relative against the float64 run of the REAL reference
+(tests/golden/train_*.npz); z / predictions, BatchNorm running statistics 1e-4 / 1e-5;
+every parameter gradient 1e-4 (relative to the tensor's largest entry) against the float64
+oracle evaluated on the ReLU branch the kernels took — see tests/test_train_emu.py for why
+the branch has to be pinned; Adam bit-near torch.optim.Adam."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+from oatomobile_b200.synthetic import synthetic_state_dict
+from tests.helpers import (TRAIN_CONFIGS, assert_close, dropout_mask, golden, grad_errors,
+                           train_inputs)
+
+pytestmark = pytest.mark.gpu
+
+
+def make_trainer(cfg, **kw):
+  import oatomobile_b200 as ob
+  from oatomobile_b200.train import Trainer
+  cls = ob.ImitativeModel if cfg["kind"] == "dim" else ob.BehaviouralModel
+  model = cls(output_shape=(cfg["T"], 2), in_channels=cfg["C"])
+  sd = synthetic_state_dict(cfg["kind"], cfg["C"], cfg["wseed"])
+  model.load_state_dict(sd, strict=True)
+  model = model.to("cuda")
+  return model, Trainer(model, **kw), sd
+
+
+def batch_of(cfg, visual, scalars):
+  dev = "cuda"
+  b = dict(visual_features=visual.to(dev), velocity=scalars[:, 0:3].to(dev),
+           is_at_traffic_light=scalars[:, 3:4].to(dev), traffic_light_state=scalars[:, 4:5].to(dev))
+  if cfg["kind"] == "cil":
+    b["mode"] = scalars[:, 5:6].to(dev)
+  return b
+
+
+def branch_of(trainer, B):
+  from tests.emu.driver import branch_from_activations
+  return branch_from_activations(lambda i: trainer.activation(i).cpu(), B)
+
+
+@pytest.mark.parametrize("name", sorted(TRAIN_CONFIGS))
+def test_forward_backward_matches_the_oracle(name):
+  cfg, gold = TRAIN_CONFIGS[name], golden(name)
+  model, trainer, sd = make_trainer(cfg)
+  assert list(model.state_dict().keys()) == list(sd.keys())  # re-homing keeps the layout
+  for k, v in model.state_dict().items():
+    assert torch.equal(v.cpu(), sd[k]), k
+  visual, scalars, target = train_inputs(cfg)
+  mask = dropout_mask(cfg)
+  loss, aux = trainer.forward_backward(batch_of(cfg, visual, scalars), target.cuda(),
+                                       dropout_mask=None if mask is None else mask.cuda())
+  assert abs(loss.item() - float(gold["loss"])) < 2e-6 * abs(float(gold["loss"]))
+  assert_close(aux, gold["aux"], tol=1e-4, what="z / predictions")
+  new_sd = model.state_dict()
+  for key in gold:
+    if key.startswith("buffer:"):
+      assert_close(new_sd[key[7:]], gold[key], tol=1e-5, what=key)
+  assert all(int(v) == 1001 for k, v in new_sd.items() if k.endswith("num_batches_tracked"))
+
+  sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+  mask64 = None if mask is None else mask.double()
+  lossb, grads64, buffers64, _ = R.train_forward_backward(
+      sd64, cfg["kind"], visual.double(), scalars.double(), target.double(), mask64,
+      branch=branch_of(trainer, cfg["B"]))
+  assert abs(lossb.item() - float(gold["loss"])) < 1e-5 * abs(float(gold["loss"]))
+  for k, v in buffers64.items():
+    assert_close(new_sd[k], v, tol=1e-5, what=k)
+  grads = {k: p.grad for k, p in model.named_parameters()}
+  assert sorted(grads) == sorted(grads64)
+  errs = grad_errors(grads, grads64)
+  worst = max(errs, key=errs.get)
+  assert errs[worst] <= 1e-4, "%s: %.2e" % (worst, errs[worst])
+  for key in gold:  # decoder-side gradients do not depend on any mask: also against the golden
+    if key.startswith("grad:") and ("_decoder" in key or "_output" in key):
+      g = torch.as_tensor(gold[key])
+      e = float((grads[key[5:]].double().cpu() - g).abs().max() / g.abs().max())
+      assert e <= 1e-4, (key, e)
+
+
+def test_cuda_and_host_execution_of_the_kernel_bodies_agree():
+  """Same functors, CUDA grid-stride launch vs host loop: launch geometry, atomics."""
+  from tests.emu.driver import EmuTrainer
+  cfg = TRAIN_CONFIGS["train_dim_T4_C2"]
+  model, trainer, sd = make_trainer(cfg)
+  visual, scalars, target = train_inputs(cfg)
+  loss, z = trainer.forward_backward(batch_of(cfg, visual, scalars), target.cuda(), dropout_mask=None)
+  emu = EmuTrainer(sd, "dim")
+  loss_e, z_e = emu.forward_backward(visual, scalars, target)
+  assert abs(loss.item() - loss_e.item()) < 2e-6 * abs(loss_e.item())
+  assert_close(z, z_e, tol=1e-5, what="z")
+  same_branch = all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+                    for a, b in zip(branch_of(trainer, cfg["B"]).values(), emu.branch(cfg["B"]).values()))
+  errs = grad_errors({k: p.grad for k, p in model.named_parameters()},
+                     {k: v.double() for k, v in emu.grads.items()})
+  worst = max(errs, key=errs.get)
+  assert errs[worst] <= (1e-4 if same_branch else 0.25), "%s: %.2e" % (worst, errs[worst])
+
+
+@pytest.mark.parametrize("name", ["train_dim_T4_C2", "train_cil_T4_C2"])
+def test_three_adam_steps_follow_the_reference_losses(name):
+  cfg, gold = TRAIN_CONFIGS[name], golden(name)
+  model, trainer, _ = make_trainer(cfg, lr=1e-3)
+  visual, scalars, target = train_inputs(cfg)
+  batch = batch_of(cfg, visual, scalars)
+  losses = []
+  for _ in range(3):
+    loss, _ = trainer.forward_backward(batch, target.cuda(), dropout_mask=None)
+    losses.append(loss.item())
+    trainer.optimizer_step()
+  assert np.allclose(losses, gold["losses"], rtol=2e-3), (losses, gold["losses"])
+
+
+def test_adam_kernel_matches_torch_optim_adam():
+  import ctypes
+  from oatomobile_b200 import _native as N
+  g = torch.Generator().manual_seed(3)
+  n = 100003
+  p0 = torch.randn(n, generator=g)
+  ref = torch.nn.Parameter(p0.clone())
+  opt = torch.optim.Adam([ref], lr=3e-3, weight_decay=0.01)
+  p, m, v = p0.cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+  ws = torch.zeros(1, dtype=torch.float64, device="cuda")
+  for step in range(1, 6):
+    grad = torch.randn(n, generator=g) * (10.0 if step == 2 else 1e-3)
+    ref.grad = grad.clone()
+    torch.nn.utils.clip_grad_norm_([ref], 1.0)
+    opt.step()
+    gd = (grad * 2.0).cuda()  # grad_scale 0.5 undoes the doubling (all-reduce SUM over 2 ranks)
+    N.check(N.lib().oat_adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, step,
+                                  3e-3, 0.9, 0.999, 1e-8, 0.01, 0.5, 1.0, ws.data_ptr(), None))
+    assert_close(p, ref.detach(), tol=2e-6, what="step %d" % step)
+
+
+@pytest.mark.parametrize("kind", ["dim", "cil"])
+def test_train_step_api_learns_and_evaluate_step_matches_the_oracle(kind):
+  """dim/train.py:175-260 / cil/train.py:168-225 surface: train_step(batch) perturbs the
+  target (DIM), samples the dropout mask, steps Adam; evaluate_step is the eval-mode loss
+  of the UPDATED weights (packed-weight cache invalidation)."""
+  cfg = dict(TRAIN_CONFIGS["train_%s_T4_C2" % kind], B=8)
+  model, trainer, _ = make_trainer(cfg, lr=1e-3, clip_gradients=(kind == "dim"))
+  visual, scalars, target = train_inputs(cfg)
+  batch = batch_of(cfg, visual, scalars)
+  batch["player_future"] = torch.cat([target, torch.zeros(cfg["B"], cfg["T"], 1)], -1).cuda()
+  torch.manual_seed(0)
+  losses = [trainer.train_step(batch).item() for _ in range(8)]
+  assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+  got = trainer.evaluate_step(batch).item()
+  sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+  vel, tl, tls = scalars[:, 0:3], scalars[:, 3:4], scalars[:, 4:5]
+  with torch.no_grad():
+    if kind == "dim":
+      z = R.imitative_params(sd, visual, vel, tl, tls)
+      _, lp, lad = R.flow_inverse(sd, target, z)
+      want = -torch.mean(lp - lad).item()
+    else:
+      pred = R.behavioural_forward(sd, cfg["T"], visual, vel, tl, tls, scalars[:, 5:6])
+      want = torch.mean(torch.sum(torch.abs(pred - target), dim=[-2, -1])).item()
+  assert abs(got - want) <= 1e-4 * max(abs(want), 1.0), (got, want)
