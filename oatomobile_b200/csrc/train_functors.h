@@ -28,6 +28,11 @@
 #else
 #define OAT_ATOMIC_ADD(p, v) (*(p) += (v))
 #endif
+#if defined(__CUDACC__)
+#define OAT_UNROLL _Pragma("unroll")
+#else
+#define OAT_UNROLL
+#endif
 
 namespace oat {
 namespace train {
@@ -42,8 +47,12 @@ OAT_HD float at(const F4& v, int i) { return (&v.x)[i]; }
 OAT_HD float relu6f(float v) { return fminf(fmaxf(v, 0.0f), 6.0f); }
 OAT_HD float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
-constexpr int kStatRows = 64;   // rows per work item in per-channel reductions
-constexpr int kGradRows = 128;  // rows per work item in weight-gradient GEMMs
+// Reductions over rows are split into chunks of `rows` rows per work item (chosen by the
+// launcher so that every reduction exposes ~150k work items) and combined with atomics.
+// Same-address atomics from many SMs serialise (~45 ns each, measured), so every such
+// accumulator exists in kReplicas copies (chunk c adds into copy c % kReplicas) that the
+// per-channel / per-element finalising work item sums and clears.
+constexpr int kReplicas = 32;
 
 // ---------------------------------------------------------------------------------
 // Stem: 3x3 stride-2 pad-1 convolution, NCHW image -> NHWC rows (perception.py:43-51)
@@ -77,30 +86,39 @@ struct StemFwd {  // gid over B*Ho*Wo*32
   }
 };
 
-struct StemBwdW {  // gid over chunks*32*(C*9); chunk = kStatRows output pixels
+struct StemBwdW {  // gid over chunks*32; chunk = `rows` output pixels; one output channel each
   const float* x;
   const float* g;  // dR [B*Ho*Wo][32]
-  float* gw;       // [32][C][3][3], pre-zeroed
-  int B, C, H, W, Ho, Wo;
+  float* gw;       // replicas [kReplicas][32*C*9], pre-zeroed (summed by ReduceReplicas)
+  int B, C, H, W, Ho, Wo, rows;
   OAT_HD void operator()(int64_t gid) const {
-    const int ct = C * 9;
-    const int tap = (int)(gid % ct);
-    const int co = (int)((gid / ct) & 31);
-    const int64_t chunk = gid / ((int64_t)ct * 32);
-    const int c = tap / 9, ky = (tap % 9) / 3, kx = tap % 3;
+    const int co = (int)(gid & 31);
+    const int64_t chunk = gid >> 5;
     const int64_t M = (int64_t)B * Ho * Wo;
-    const int64_t m0 = chunk * kStatRows;
-    const int64_t m1 = m0 + kStatRows < M ? m0 + kStatRows : M;
-    float acc = 0.0f;
-    for (int64_t m = m0; m < m1; ++m) {
-      const int ox = (int)(m % Wo);
-      const int oy = (int)((m / Wo) % Ho);
-      const int b = (int)(m / ((int64_t)Wo * Ho));
-      const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
-      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-      acc = fmaf(g[m * 32 + co], x[(((int64_t)b * C + c) * H + iy) * W + ix], acc);
+    const int64_t m0 = chunk * rows;
+    const int64_t m1 = m0 + rows < M ? m0 + rows : M;
+    float* dst = gw + (chunk % kReplicas) * (int64_t)(32 * C * 9) + co * C * 9;
+    for (int c = 0; c < C; ++c) {
+      float acc[9] = {};
+      for (int64_t m = m0; m < m1; ++m) {
+        const int ox = (int)(m % Wo);
+        const int oy = (int)((m / Wo) % Ho);
+        const int b = (int)(m / ((int64_t)Wo * Ho));
+        const float gv = g[m * 32 + co];
+        const float* xp = x + ((int64_t)b * C + c) * H * W;
+        OAT_UNROLL
+        for (int ky = 0; ky < 3; ++ky) {
+          const int iy = oy * 2 - 1 + ky;
+          OAT_UNROLL
+          for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * 2 - 1 + kx;
+            const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+            acc[ky * 3 + kx] = fmaf(gv, in ? xp[iy * W + ix] : 0.0f, acc[ky * 3 + kx]);
+          }
+        }
+      }
+      for (int t = 0; t < 9; ++t) OAT_ATOMIC_ADD(dst + c * 9 + t, acc[t]);
     }
-    OAT_ATOMIC_ADD(gw + (co * C + c) * 9 + ky * 3 + kx, acc);
   }
 };
 
@@ -183,14 +201,14 @@ struct PwBwdW {  // gW[n][k] += sum_{m in chunk} G[m][n] A[m][k];  gid over chun
   const float* a;
   float* gw;  // pre-zeroed
   int64_t M;
-  int N, K;
+  int N, K, rows;
   OAT_HD void operator()(int64_t gid) const {
     const int kt = K >> 2, nt = N >> 2;
     const int k0 = (int)(gid % kt) << 2;
     const int n0 = (int)((gid / kt) % nt) << 2;
     const int64_t chunk = gid / ((int64_t)kt * nt);
-    const int64_t m0 = chunk * kGradRows;
-    const int64_t m1 = m0 + kGradRows < M ? m0 + kGradRows : M;
+    const int64_t m0 = chunk * rows;
+    const int64_t m1 = m0 + rows < M ? m0 + rows : M;
     float acc[4][4] = {};
     for (int64_t m = m0; m < m1; ++m) {
       const F4 gv = ld4(g + m * N + n0);
@@ -277,18 +295,18 @@ struct DwBwdX {  // gid over B*H*W*(C/4); dA written (the expanded tensor has on
   }
 };
 
-struct DwBwdW {  // gid over chunks*(C/4); chunk = kStatRows output pixels
+struct DwBwdW {  // gid over chunks*(C/4); chunk = `rows` output pixels
   const float* g;
   const float* a;
-  float* gw;  // [C][9], pre-zeroed
-  int B, H, W, Ho, Wo, C, stride;
+  float* gw;  // replicas [kReplicas][C*9], pre-zeroed (summed by ReduceReplicas)
+  int B, H, W, Ho, Wo, C, stride, rows;
   OAT_HD void operator()(int64_t gid) const {
     const int ct = C >> 2;
     const int c0 = (int)(gid % ct) << 2;
     const int64_t chunk = gid / ct;
     const int64_t M = (int64_t)B * Ho * Wo;
-    const int64_t m0 = chunk * kStatRows;
-    const int64_t m1 = m0 + kStatRows < M ? m0 + kStatRows : M;
+    const int64_t m0 = chunk * rows;
+    const int64_t m1 = m0 + rows < M ? m0 + rows : M;
     float acc[4][9] = {};
     for (int64_t m = m0; m < m1; ++m) {
       const int ox = (int)(m % Wo);
@@ -310,8 +328,27 @@ struct DwBwdW {  // gid over chunks*(C/4); chunk = kStatRows output pixels
         }
       }
     }
+    float* dst = gw + (chunk % kReplicas) * (int64_t)(C * 9);
     for (int i = 0; i < 4; ++i)
-      for (int t = 0; t < 9; ++t) OAT_ATOMIC_ADD(gw + (c0 + i) * 9 + t, acc[i][t]);
+      for (int t = 0; t < 9; ++t) OAT_ATOMIC_ADD(dst + (c0 + i) * 9 + t, acc[i][t]);
+  }
+};
+
+struct ReduceReplicas {  // gid over n: out[i] = sum_r rep[r][i]; clears the replicas
+  float* rep;
+  float* out;
+  int64_t n;
+  OAT_HD void operator()(int64_t i) const {
+    float v[kReplicas];
+    OAT_UNROLL
+    for (int r = 0; r < kReplicas; ++r) v[r] = rep[r * n + i];
+    float s = 0.0f;
+    OAT_UNROLL
+    for (int r = 0; r < kReplicas; ++r) {
+      s += v[r];
+      rep[r * n + i] = 0.0f;
+    }
+    out[i] = s;
   }
 };
 
@@ -319,60 +356,60 @@ struct DwBwdW {  // gid over chunks*(C/4); chunk = kStatRows output pixels
 // BatchNorm2d in training mode (eps 1e-5, momentum 0.1, biased variance for the
 // normalisation, unbiased for the running estimate — torch.nn.BatchNorm2d)
 // ---------------------------------------------------------------------------------
-struct BnSum {  // gid over chunks*(C/4): acc[c] += sum_rows (R - shift)^pow
+struct BnStats {  // gid over chunks*(C/4): acc[c] += sum R, acc[C+c] += sum R^2 (double)
   const float* r;
-  const float* shift;  // per-channel mean for the variance pass, null for the mean pass
-  double* acc;         // [C], pre-zeroed
+  double* acc;  // [kReplicas][2C], pre-zeroed
   int64_t M;
-  int C;
+  int C, rows;
   OAT_HD void operator()(int64_t gid) const {
     const int ct = C >> 2;
     const int c0 = (int)(gid % ct) << 2;
-    const int64_t m0 = (gid / ct) * kStatRows;
-    const int64_t m1 = m0 + kStatRows < M ? m0 + kStatRows : M;
-    F4 s{0, 0, 0, 0};
-    if (shift == nullptr) {
-      for (int64_t m = m0; m < m1; ++m) {
-        const F4 v = ld4(r + m * C + c0);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
-    } else {
-      const F4 mu = ld4(shift + c0);
-      for (int64_t m = m0; m < m1; ++m) {
-        const F4 v = ld4(r + m * C + c0);
-        const float dx = v.x - mu.x, dy = v.y - mu.y, dz = v.z - mu.z, dw = v.w - mu.w;
-        s.x = fmaf(dx, dx, s.x); s.y = fmaf(dy, dy, s.y);
-        s.z = fmaf(dz, dz, s.z); s.w = fmaf(dw, dw, s.w);
+    const int64_t m0 = (gid / ct) * rows;
+    const int64_t m1 = m0 + rows < M ? m0 + rows : M;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (int64_t m = m0; m < m1; ++m) {
+      const F4 v = ld4(r + m * C + c0);
+      for (int i = 0; i < 4; ++i) {
+        const double x = (double)at(v, i);
+        s1[i] += x;
+        s2[i] += x * x;
       }
     }
-    for (int i = 0; i < 4; ++i) OAT_ATOMIC_ADD(acc + c0 + i, (double)at(s, i));
+    double* dst = acc + ((gid / ct) % kReplicas) * 2 * C;
+    for (int i = 0; i < 4; ++i) {
+      OAT_ATOMIC_ADD(dst + c0 + i, s1[i]);
+      OAT_ATOMIC_ADD(dst + C + c0 + i, s2[i]);
+    }
   }
 };
 
-struct BnMean {  // gid over C
+OAT_HD double drain_replicas(double* acc, int64_t index, int64_t stride) {
+  double v[kReplicas];
+  OAT_UNROLL
+  for (int r = 0; r < kReplicas; ++r) v[r] = acc[r * stride + index];  // independent loads first
+  double s = 0.0;
+  OAT_UNROLL
+  for (int r = 0; r < kReplicas; ++r) {
+    s += v[r];
+    acc[r * stride + index] = 0.0;
+  }
+  return s;
+}
+
+struct BnFinalize {  // gid over C: batch mean / 1/sqrt(var+eps), running estimates, clears acc
   double* acc;
-  float* mean;
-  float* running_mean;
+  float *mean, *invstd, *running_mean, *running_var;
   int64_t M;
+  int C;
   OAT_HD void operator()(int64_t c) const {
-    const double mu = acc[c] / (double)M;
+    const double mu = drain_replicas(acc, c, 2 * C) / (double)M;
+    double var = drain_replicas(acc, C + c, 2 * C) / (double)M - mu * mu;  // sums are exact in double
+    if (var < 0.0) var = 0.0;
     mean[c] = (float)mu;
-    running_mean[c] = (float)(0.9 * (double)running_mean[c] + 0.1 * mu);
-    acc[c] = 0.0;
-  }
-};
-
-struct BnVar {  // gid over C
-  double* acc;
-  float* invstd;
-  float* running_var;
-  int64_t M;
-  OAT_HD void operator()(int64_t c) const {
-    const double var = acc[c] / (double)M;
     invstd[c] = (float)(1.0 / sqrt(var + 1e-5));
-    const double unbiased = M > 1 ? acc[c] / (double)(M - 1) : var;
+    const double unbiased = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+    running_mean[c] = (float)(0.9 * (double)running_mean[c] + 0.1 * mu);
     running_var[c] = (float)(0.9 * (double)running_var[c] + 0.1 * unbiased);
-    acc[c] = 0.0;
   }
 };
 
@@ -406,14 +443,14 @@ struct BnBwdReduce {  // gid over chunks*(C/4): acc[c] += sum dP, acc[C+c] += su
   const float* r;
   const float* g;  // dA
   const float *mean, *invstd, *gamma, *beta;
-  double* acc;  // [2C], pre-zeroed
+  double* acc;  // [kReplicas][2C], pre-zeroed
   int64_t M;
-  int C, relu6;
+  int C, relu6, rows;
   OAT_HD void operator()(int64_t gid) const {
     const int ct = C >> 2;
     const int c0 = (int)(gid % ct) << 2;
-    const int64_t m0 = (gid / ct) * kStatRows;
-    const int64_t m1 = m0 + kStatRows < M ? m0 + kStatRows : M;
+    const int64_t m0 = (gid / ct) * rows;
+    const int64_t m1 = m0 + rows < M ? m0 + rows : M;
     const F4 mu = ld4(mean + c0), is = ld4(invstd + c0), ga = ld4(gamma + c0), be = ld4(beta + c0);
     F4 s1{0, 0, 0, 0}, s2{0, 0, 0, 0};
     for (int64_t m = m0; m < m1; ++m) {
@@ -429,9 +466,10 @@ struct BnBwdReduce {  // gid over chunks*(C/4): acc[c] += sum dP, acc[C+c] += su
         at(s2, i) = fmaf(dp, xh, at(s2, i));
       }
     }
+    double* dst = acc + ((gid / ct) % kReplicas) * 2 * C;
     for (int i = 0; i < 4; ++i) {
-      OAT_ATOMIC_ADD(acc + c0 + i, (double)at(s1, i));
-      OAT_ATOMIC_ADD(acc + C + c0 + i, (double)at(s2, i));
+      OAT_ATOMIC_ADD(dst + c0 + i, (double)at(s1, i));
+      OAT_ATOMIC_ADD(dst + C + c0 + i, (double)at(s2, i));
     }
   }
 };
@@ -443,12 +481,11 @@ struct BnBwdParams {  // gid over C
   int64_t M;
   int C;
   OAT_HD void operator()(int64_t c) const {
-    gbeta[c] = (float)acc[c];
-    ggamma[c] = (float)acc[C + c];
-    mean_dp[c] = (float)(acc[c] / (double)M);
-    mean_dpxh[c] = (float)(acc[C + c] / (double)M);
-    acc[c] = 0.0;
-    acc[C + c] = 0.0;
+    const double s1 = drain_replicas(acc, c, 2 * C), s2 = drain_replicas(acc, C + c, 2 * C);
+    gbeta[c] = (float)s1;
+    ggamma[c] = (float)s2;
+    mean_dp[c] = (float)(s1 / (double)M);
+    mean_dpxh[c] = (float)(s2 / (double)M);
   }
 };
 
@@ -591,51 +628,75 @@ struct CopyCols {  // dst[m][off + j] = src[m][j];  gid over M*S
 };
 
 // ---------------------------------------------------------------------------------
-// Decoders.  One work item = one batch row, forward then reverse sweep; the per-step
-// record lives in a scratch buffer [B][T][kDecRecord].
+// Decoders.  Pass 1: one work item per batch row runs the recurrence forward and the
+// reverse sweep, leaving per-(row, step) records in a scratch buffer [B][T][kDecRecord].
+// Pass 2: the parameter gradients are reductions of outer products over those records,
+// one work item per output element, summed in a fixed order (deterministic, no atomics).
 // GRUCell (torch gate order r|z|n):  r = s(Wir u + bir + Whr h + bhr), g = s(...z...),
 // n = tanh(Win u + bin + r * (Whn h + bhn)),  h' = (1-g) n + g h.
 // ---------------------------------------------------------------------------------
-constexpr int kDecRecord = 64 * 5 + 32 + 8;  // h_prev | r | g | n | hn | a1 | misc
+// record layout (floats)
+constexpr int kRecH = 0;       // h_prev [64]
+constexpr int kRecR = 64;      // r [64]
+constexpr int kRecG = 128;     // g (update gate) [64]
+constexpr int kRecN = 192;     // n [64]
+constexpr int kRecHn = 256;    // Whn h + bhn [64]
+constexpr int kRecA1 = 320;    // DIM head hidden layer, post-ReLU [32]
+constexpr int kRecMisc = 352;  // DIM: x0 x1 sigma0 sigma1 sraw0 sraw1 u0 u1; CIL: u0 u1 sign0 sign1
+constexpr int kRecHcur = 360;  // h' of this step [64]
+constexpr int kRecDgi = 424;   // d loss / d (W_ih u + b_ih) [192]
+constexpr int kRecDgh = 616;   // d loss / d (W_hh h + b_hh) [192]
+constexpr int kRecDa1 = 808;   // DIM: d loss / d (head pre-activation), ReLU-masked [32]
+constexpr int kRecDout = 840;  // DIM: d loss / d o [4]; CIL: d loss / d (W_o h + b_o) [2]
+constexpr int kDecRecord = 848;
 
 struct DecParams {
   const float *wih, *whh, *bih, *bhh;  // [192][2], [192][64], [192], [192]
   const float *w1, *b1, *w2, *b2;      // DIM head [32][64],[32],[4][32],[4]; CIL: w1=[2][64], b1=[2]
-  float *gwih, *gwhh, *gbih, *gbhh, *gw1, *gb1, *gw2, *gb2;  // pre-zeroed
+  float *gwih, *gwhh, *gbih, *gbhh, *gw1, *gb1, *gw2, *gb2;
 };
 
-OAT_HD void gru_forward(const DecParams& p, const float* u, const float* h, float* rec, float* hn) {
-  // rec: h_prev[64] | r[64] | g[64] | n[64] | hn_pre[64]
+OAT_HD void gru_forward(const DecParams& p, const float* u, const float* h, float* rec) {
   for (int j = 0; j < 64; ++j) {
-    float ar = p.bhh[j], ag = p.bhh[64 + j], an = p.bhh[128 + j];
+    // two partial sums per gate and float4 weight loads: six independent FMA chains
+    float ar = p.bhh[j], ag = p.bhh[64 + j], an = p.bhh[128 + j], ar2 = 0.0f, ag2 = 0.0f, an2 = 0.0f;
     const float *wr = p.whh + j * 64, *wg = p.whh + (64 + j) * 64, *wn = p.whh + (128 + j) * 64;
-    for (int k = 0; k < 64; ++k) {
-      ar = fmaf(wr[k], h[k], ar);
-      ag = fmaf(wg[k], h[k], ag);
-      an = fmaf(wn[k], h[k], an);
+    OAT_UNROLL
+    for (int k = 0; k < 64; k += 4) {
+      const F4 a = ld4(wr + k), b = ld4(wg + k), c = ld4(wn + k);
+      ar = fmaf(a.x, h[k], ar); ar2 = fmaf(a.y, h[k + 1], ar2);
+      ar = fmaf(a.z, h[k + 2], ar); ar2 = fmaf(a.w, h[k + 3], ar2);
+      ag = fmaf(b.x, h[k], ag); ag2 = fmaf(b.y, h[k + 1], ag2);
+      ag = fmaf(b.z, h[k + 2], ag); ag2 = fmaf(b.w, h[k + 3], ag2);
+      an = fmaf(c.x, h[k], an); an2 = fmaf(c.y, h[k + 1], an2);
+      an = fmaf(c.z, h[k + 2], an); an2 = fmaf(c.w, h[k + 3], an2);
     }
+    ar += ar2;
+    ag += ag2;
+    an += an2;
     const float ir = fmaf(p.wih[j * 2 + 1], u[1], fmaf(p.wih[j * 2], u[0], p.bih[j]));
     const float ig = fmaf(p.wih[(64 + j) * 2 + 1], u[1], fmaf(p.wih[(64 + j) * 2], u[0], p.bih[64 + j]));
     const float in = fmaf(p.wih[(128 + j) * 2 + 1], u[1], fmaf(p.wih[(128 + j) * 2], u[0], p.bih[128 + j]));
     const float r = sigmoidf_(ir + ar), g = sigmoidf_(ig + ag);
     const float n = tanhf(fmaf(r, an, in));
-    rec[j] = h[j];
-    rec[64 + j] = r;
-    rec[128 + j] = g;
-    rec[192 + j] = n;
-    rec[256 + j] = an;
-    hn[j] = fmaf(g, h[j] - n, n);  // (1-g) n + g h
+    rec[kRecH + j] = h[j];
+    rec[kRecR + j] = r;
+    rec[kRecG + j] = g;
+    rec[kRecN + j] = n;
+    rec[kRecHn + j] = an;
+    rec[kRecHcur + j] = fmaf(g, h[j] - n, n);  // (1-g) n + g h
   }
 }
 
-// Consumes dh (gradient wrt the step's output state), accumulates parameter gradients,
-// overwrites dh with the gradient wrt the previous state; returns d(loss)/d(u) in du.
-OAT_HD void gru_backward(const DecParams& p, const float* u, const float* rec, float* dh, float* du) {
+// Consumes dh (gradient wrt the step's output state), stores the gate gradients in the
+// record, overwrites dh with the gradient wrt the previous state, returns d loss / d u.
+OAT_HD void gru_backward(const DecParams& p, float* rec, float* dh, float* du) {
   float dh_prev[64];
   for (int k = 0; k < 64; ++k) dh_prev[k] = 0.0f;
   du[0] = du[1] = 0.0f;
   for (int j = 0; j < 64; ++j) {
-    const float h = rec[j], r = rec[64 + j], g = rec[128 + j], n = rec[192 + j], an = rec[256 + j];
+    const float h = rec[kRecH + j], r = rec[kRecR + j], g = rec[kRecG + j], n = rec[kRecN + j],
+                an = rec[kRecHn + j];
     const float d = dh[j];
     const float dn_pre = d * (1.0f - g) * (1.0f - n * n);
     const float dg_pre = d * (h - n) * g * (1.0f - g);
@@ -646,17 +707,18 @@ OAT_HD void gru_backward(const DecParams& p, const float* u, const float* rec, f
     const float gh[3] = {dr_pre, dg_pre, dhn};
     for (int q = 0; q < 3; ++q) {
       const int row = q * 64 + j;
-      OAT_ATOMIC_ADD(p.gbih + row, gi[q]);
-      OAT_ATOMIC_ADD(p.gbhh + row, gh[q]);
-      OAT_ATOMIC_ADD(p.gwih + row * 2, gi[q] * u[0]);
-      OAT_ATOMIC_ADD(p.gwih + row * 2 + 1, gi[q] * u[1]);
+      rec[kRecDgi + row] = gi[q];
+      rec[kRecDgh + row] = gh[q];
       du[0] = fmaf(gi[q], p.wih[row * 2], du[0]);
       du[1] = fmaf(gi[q], p.wih[row * 2 + 1], du[1]);
       const float* wrow = p.whh + row * 64;
-      float* grow = p.gwhh + row * 64;
-      for (int k = 0; k < 64; ++k) {
-        OAT_ATOMIC_ADD(grow + k, gh[q] * rec[k]);
-        dh_prev[k] = fmaf(gh[q], wrow[k], dh_prev[k]);
+      OAT_UNROLL
+      for (int k = 0; k < 64; k += 4) {
+        const F4 wv = ld4(wrow + k);
+        dh_prev[k] = fmaf(gh[q], wv.x, dh_prev[k]);
+        dh_prev[k + 1] = fmaf(gh[q], wv.y, dh_prev[k + 1]);
+        dh_prev[k + 2] = fmaf(gh[q], wv.z, dh_prev[k + 2]);
+        dh_prev[k + 3] = fmaf(gh[q], wv.w, dh_prev[k + 3]);
       }
     }
   }
@@ -672,7 +734,7 @@ struct DimNllStep {  // gid over B: loss = -mean_b(log_prob - logabsdet) (dim/tr
   double* loss;    // accumulates the batch SUM of row losses; pre-zeroed
   int B, T;
   OAT_HD void operator()(int64_t b) const {
-    float h[64], hn[64];
+    float h[64];
     for (int k = 0; k < 64; ++k) h[k] = z[b * 64 + k];
     float* rec0 = scratch + b * T * kDecRecord;
     const float* yb = y + b * T * 2;
@@ -680,14 +742,23 @@ struct DimNllStep {  // gid over B: loss = -mean_b(log_prob - logabsdet) (dim/tr
     float row_loss = (float)T * 1.8378770664093453f;  // T * log(2 pi)
     for (int t = 0; t < T; ++t) {
       float* rec = rec0 + t * kDecRecord;
+      float* misc = rec + kRecMisc;
       float u[2] = {0.0f, 0.0f};
       if (t > 0) { u[0] = yb[(t - 1) * 2]; u[1] = yb[(t - 1) * 2 + 1]; }
-      gru_forward(p, u, h, rec, hn);
-      float* a1 = rec + 320;
+      misc[6] = u[0];
+      misc[7] = u[1];
+      gru_forward(p, u, h, rec);
+      const float* hn = rec + kRecHcur;
+      float* a1 = rec + kRecA1;
       for (int j = 0; j < 32; ++j) {
-        float acc = p.b1[j];
-        for (int k = 0; k < 64; ++k) acc = fmaf(p.w1[j * 64 + k], hn[k], acc);
-        a1[j] = fmaxf(acc, 0.0f);
+        float acc = p.b1[j], acc2 = 0.0f;
+        OAT_UNROLL
+        for (int k = 0; k < 64; k += 4) {
+          const F4 wv = ld4(p.w1 + j * 64 + k);
+          acc = fmaf(wv.x, hn[k], acc); acc2 = fmaf(wv.y, hn[k + 1], acc2);
+          acc = fmaf(wv.z, hn[k + 2], acc); acc2 = fmaf(wv.w, hn[k + 3], acc2);
+        }
+        a1[j] = fmaxf(acc + acc2, 0.0f);
       }
       float o[4];
       for (int i = 0; i < 4; ++i) {
@@ -695,7 +766,6 @@ struct DimNllStep {  // gid over B: loss = -mean_b(log_prob - logabsdet) (dim/tr
         for (int j = 0; j < 32; ++j) acc = fmaf(p.w2[i * 32 + j], a1[j], acc);
         o[i] = acc;
       }
-      float* misc = rec + 352;  // x0 x1 sigma0 sigma1 sraw0 sraw1
       for (int d = 0; d < 2; ++d) {
         const float mu = u[d] + o[d];
         const float sraw = o[2 + d];
@@ -714,48 +784,36 @@ struct DimNllStep {  // gid over B: loss = -mean_b(log_prob - logabsdet) (dim/tr
     float dh[64];
     for (int k = 0; k < 64; ++k) dh[k] = 0.0f;
     for (int t = T - 1; t >= 0; --t) {
-      const float* rec = rec0 + t * kDecRecord;
-      const float* a1 = rec + 320;
-      const float* misc = rec + 352;
-      float u[2] = {0.0f, 0.0f};
-      if (t > 0) { u[0] = yb[(t - 1) * 2]; u[1] = yb[(t - 1) * 2 + 1]; }
-      // h' of this step = h_prev of the next record (or recompute for the last step)
-      float hcur[64];
-      if (t + 1 < T) {
-        for (int k = 0; k < 64; ++k) hcur[k] = rec0[(t + 1) * kDecRecord + k];
-      } else {
-        for (int k = 0; k < 64; ++k) {
-          const float g = rec[128 + k], n = rec[192 + k];
-          hcur[k] = fmaf(g, rec[k] - n, n);
-        }
-      }
+      float* rec = rec0 + t * kDecRecord;
+      const float* a1 = rec + kRecA1;
+      const float* misc = rec + kRecMisc;
       float dout[4];
       for (int d = 0; d < 2; ++d) {
         const float x = misc[d], sigma = misc[2 + d], sraw = misc[4 + d];
         const float dx = x * invB;
-        dout[d] = -dx / sigma;                                  // d/d mu
-        const float dsigma = (invB - dx * x) / sigma;           // log sigma term + x = (y-mu)/sigma
+        dout[d] = -dx / sigma;                         // d/d mu
+        const float dsigma = (invB - dx * x) / sigma;  // log sigma term + x = (y-mu)/sigma
         dout[2 + d] = dsigma * (sraw > 20.0f ? 1.0f : sigmoidf_(sraw));
       }
-      float da1[32];
-      for (int j = 0; j < 32; ++j) da1[j] = 0.0f;
-      for (int i = 0; i < 4; ++i) {
-        OAT_ATOMIC_ADD(p.gb2 + i, dout[i]);
-        for (int j = 0; j < 32; ++j) {
-          OAT_ATOMIC_ADD(p.gw2 + i * 32 + j, dout[i] * a1[j]);
-          da1[j] = fmaf(dout[i], p.w2[i * 32 + j], da1[j]);
-        }
-      }
+      for (int i = 0; i < 4; ++i) rec[kRecDout + i] = dout[i];
       for (int j = 0; j < 32; ++j) {
-        if (!(a1[j] > 0.0f)) continue;
-        OAT_ATOMIC_ADD(p.gb1 + j, da1[j]);
-        for (int k = 0; k < 64; ++k) {
-          OAT_ATOMIC_ADD(p.gw1 + j * 64 + k, da1[j] * hcur[k]);
-          dh[k] = fmaf(da1[j], p.w1[j * 64 + k], dh[k]);
+        float da = 0.0f;
+        for (int i = 0; i < 4; ++i) da = fmaf(dout[i], p.w2[i * 32 + j], da);
+        if (!(a1[j] > 0.0f)) da = 0.0f;
+        rec[kRecDa1 + j] = da;
+        if (da != 0.0f) {
+          OAT_UNROLL
+          for (int k = 0; k < 64; k += 4) {
+            const F4 wv = ld4(p.w1 + j * 64 + k);
+            dh[k] = fmaf(da, wv.x, dh[k]);
+            dh[k + 1] = fmaf(da, wv.y, dh[k + 1]);
+            dh[k + 2] = fmaf(da, wv.z, dh[k + 2]);
+            dh[k + 3] = fmaf(da, wv.w, dh[k + 3]);
+          }
         }
       }
       float du[2];
-      gru_backward(p, u, rec, dh, du);  // inputs are data: du is discarded
+      gru_backward(p, rec, dh, du);  // inputs are data: du is discarded
     }
     for (int k = 0; k < 64; ++k) gz[b * 64 + k] = dh[k];
   }
@@ -771,7 +829,7 @@ struct CilL1Step {  // gid over B: loss = mean_b sum_{t,d} |x_t - y_t| (cil/trai
   double* loss;
   int B, T;
   OAT_HD void operator()(int64_t b) const {
-    float h[64], hn[64];
+    float h[64];
     for (int k = 0; k < 64; ++k) h[k] = z[b * 64 + k];
     float* rec0 = scratch + b * T * kDecRecord;
     const float* yb = y + b * T * 2;
@@ -780,10 +838,11 @@ struct CilL1Step {  // gid over B: loss = mean_b sum_{t,d} |x_t - y_t| (cil/trai
     float row_loss = 0.0f;
     for (int t = 0; t < T; ++t) {
       float* rec = rec0 + t * kDecRecord;
-      float* misc = rec + 352;  // u0 u1 sign0 sign1
+      float* misc = rec + kRecMisc;
       misc[0] = x[0];
       misc[1] = x[1];
-      gru_forward(p, x, h, rec, hn);
+      gru_forward(p, x, h, rec);
+      const float* hn = rec + kRecHcur;
       for (int d = 0; d < 2; ++d) {
         float acc = p.b1[d];
         for (int k = 0; k < 64; ++k) acc = fmaf(p.w1[d * 64 + k], hn[k], acc);
@@ -801,31 +860,84 @@ struct CilL1Step {  // gid over B: loss = mean_b sum_{t,d} |x_t - y_t| (cil/trai
     for (int k = 0; k < 64; ++k) dh[k] = 0.0f;
     float dx[2] = {0.0f, 0.0f};  // gradient wrt x_t flowing back from later steps
     for (int t = T - 1; t >= 0; --t) {
-      const float* rec = rec0 + t * kDecRecord;
-      const float* misc = rec + 352;
-      float hcur[64];
-      if (t + 1 < T) {
-        for (int k = 0; k < 64; ++k) hcur[k] = rec0[(t + 1) * kDecRecord + k];
-      } else {
-        for (int k = 0; k < 64; ++k) {
-          const float g = rec[128 + k], n = rec[192 + k];
-          hcur[k] = fmaf(g, rec[k] - n, n);
-        }
-      }
+      float* rec = rec0 + t * kDecRecord;
+      const float* misc = rec + kRecMisc;
       for (int d = 0; d < 2; ++d) {
         dx[d] += misc[2 + d] * invB;  // x_t = x_{t-1} + W_o h_t + b_o
-        OAT_ATOMIC_ADD(p.gb1 + d, dx[d]);
-        for (int k = 0; k < 64; ++k) {
-          OAT_ATOMIC_ADD(p.gw1 + d * 64 + k, dx[d] * hcur[k]);
-          dh[k] = fmaf(dx[d], p.w1[d * 64 + k], dh[k]);
-        }
+        rec[kRecDout + d] = dx[d];
+        for (int k = 0; k < 64; ++k) dh[k] = fmaf(dx[d], p.w1[d * 64 + k], dh[k]);
       }
-      float u[2] = {misc[0], misc[1]}, du[2];
-      gru_backward(p, u, rec, dh, du);
+      float du[2];
+      gru_backward(p, rec, dh, du);
       dx[0] += du[0];  // x_{t-1} also feeds the GRU input of step t
       dx[1] += du[1];
     }
     for (int k = 0; k < 64; ++k) gz[b * 64 + k] = dh[k];
+  }
+};
+
+// ---- pass 2: parameter gradients = sums of outer products over the B*T records ----
+struct DecGradWhh {  // gid over 192*64: gW_hh[row][k] = sum dgh[row] * h_prev[k]
+  const float* scratch;
+  float* gwhh;
+  int64_t records;  // B*T
+  OAT_HD void operator()(int64_t gid) const {
+    const int k = (int)(gid & 63), row = (int)(gid >> 6);
+    float acc = 0.0f;
+    for (int64_t i = 0; i < records; ++i) {
+      const float* rec = scratch + i * kDecRecord;
+      acc = fmaf(rec[kRecDgh + row], rec[kRecH + k], acc);
+    }
+    gwhh[gid] = acc;
+  }
+};
+
+struct DecGradIh {  // gid over 192*4: gW_ih[row][0..1], gb_ih[row], gb_hh[row]
+  const float* scratch;
+  float *gwih, *gbih, *gbhh;
+  int64_t records;
+  int u_off;  // where the step's GRU input lives in the record
+  OAT_HD void operator()(int64_t gid) const {
+    const int col = (int)(gid & 3), row = (int)(gid >> 2);
+    float acc = 0.0f;
+    for (int64_t i = 0; i < records; ++i) {
+      const float* rec = scratch + i * kDecRecord;
+      if (col < 2) acc = fmaf(rec[kRecDgi + row], rec[u_off + col], acc);
+      else acc += col == 2 ? rec[kRecDgi + row] : rec[kRecDgh + row];
+    }
+    if (col < 2) gwih[row * 2 + col] = acc;
+    else if (col == 2) gbih[row] = acc;
+    else gbhh[row] = acc;
+  }
+};
+
+struct DecGradHead {  // gid over n1*65 + n2*33 (n2 = 0 for CIL)
+  // DIM: gW1[j][k] = sum da1[j] hcur[k], gb1 (n1 = 32); gW2[i][j] = sum dout[i] a1[j], gb2 (n2 = 4)
+  // CIL: gW_o[d][k] = sum dx[d] hcur[k], gb_o (n1 = 2, the "da1" slot is kRecDout)
+  const float* scratch;
+  float *gw1, *gb1, *gw2, *gb2;
+  int64_t records;
+  int n1, n2, d1_off;
+  OAT_HD void operator()(int64_t gid) const {
+    float acc = 0.0f;
+    if (gid < (int64_t)n1 * 65) {
+      const int k = (int)(gid % 65), j = (int)(gid / 65);
+      for (int64_t i = 0; i < records; ++i) {
+        const float* rec = scratch + i * kDecRecord;
+        acc = fmaf(rec[d1_off + j], k < 64 ? rec[kRecHcur + k] : 1.0f, acc);
+      }
+      if (k < 64) gw1[j * 64 + k] = acc;
+      else gb1[j] = acc;
+    } else {
+      const int64_t e = gid - (int64_t)n1 * 65;
+      const int j = (int)(e % 33), i2 = (int)(e / 33);
+      for (int64_t i = 0; i < records; ++i) {
+        const float* rec = scratch + i * kDecRecord;
+        acc = fmaf(rec[kRecDout + i2], j < 32 ? rec[kRecA1 + j] : 1.0f, acc);
+      }
+      if (j < 32) gw2[i2 * 32 + j] = acc;
+      else gb2[i2] = acc;
+    }
   }
 };
 

@@ -59,6 +59,7 @@ struct TrainerT {
   float *pooled = nullptr, *gpooled = nullptr, *U = nullptr, *gU = nullptr;
   float *H1 = nullptr, *H2 = nullptr, *Z = nullptr, *gH1 = nullptr, *gH2 = nullptr, *gZ = nullptr;
   float* scratch = nullptr;
+  float* wrep = nullptr;  // kReplicas copies of the largest depthwise / stem weight gradient
   double* loss_acc = nullptr;
   int64_t work_items = 0;  // functor launches of the last step (gpu_launches accounting)
 
@@ -102,6 +103,10 @@ struct TrainerT {
       return false;
     }
     C = (int)st->second.shape[1];
+    if (C < 1 || C > 8) {
+      err = "stem conv must be [32,C,3,3] with 1 <= C <= 8";
+      return false;
+    }
     Unit stem;
     stem.type = kStem;
     stem.cin = C; stem.cout = 32; stem.stride = 2; stem.hin = H; stem.hout = (H - 1) / 2 + 1;
@@ -187,7 +192,7 @@ struct TrainerT {
       ok = ok && (u.R = alloc<float>(n)) && (u.A = alloc<float>(n)) && (u.G = alloc<float>(n));
       ok = ok && (u.mean = alloc<float>(u.cout)) && (u.invstd = alloc<float>(u.cout)) &&
            (u.mdp = alloc<float>(u.cout)) && (u.mdpxh = alloc<float>(u.cout)) &&
-           (u.acc = alloc<double>(2 * (size_t)u.cout));
+           (u.acc = alloc<double>(2 * (size_t)u.cout * kReplicas));
       if (!ok) break;
     }
     const int in0 = 128 + S;
@@ -196,7 +201,8 @@ struct TrainerT {
          (H1 = alloc<float>((size_t)B * 64)) && (H2 = alloc<float>((size_t)B * 64)) &&
          (Z = alloc<float>((size_t)B * 64)) && (gH1 = alloc<float>((size_t)B * 64)) &&
          (gH2 = alloc<float>((size_t)B * 64)) && (gZ = alloc<float>((size_t)B * 64)) &&
-         (scratch = alloc<float>((size_t)B * T * kDecRecord)) && (loss_acc = alloc<double>(1));
+         (scratch = alloc<float>((size_t)B * T * kDecRecord)) && (loss_acc = alloc<double>(1)) &&
+         (wrep = alloc<float>((size_t)kReplicas * 960 * 9));
     if (!ok) {
       release();
       err = "out of device memory reserving the training workspace";
@@ -234,13 +240,20 @@ struct TrainerT {
     ++work_items;
   }
   static int64_t chunks(int64_t M, int rows) { return (M + rows - 1) / rows; }
+  // Rows per work item of a row reduction with `per_chunk` work items per chunk: aim at
+  // ~150k work items in total, between `lo` and `hi` rows each.
+  static int pick_rows(int64_t M, int64_t per_chunk, int lo, int hi) {
+    int64_t r = (M * per_chunk + 150000 - 1) / 150000;
+    if (r < lo) r = lo;
+    if (r > hi) r = hi;
+    return (int)r;
+  }
 
   void batchnorm_forward(Unit& u, int64_t M) {
     const int c = u.cout;
-    run(chunks(M, kStatRows) * (c / 4), BnSum{u.R, nullptr, u.acc, M, c});
-    run(c, BnMean{u.acc, u.mean, u.rmean.p, M});
-    run(chunks(M, kStatRows) * (c / 4), BnSum{u.R, u.mean, u.acc, M, c});
-    run(c, BnVar{u.acc, u.invstd, u.rvar.p, M});
+    const int rows = pick_rows(M, c / 4, 16, 128);
+    run(chunks(M, rows) * (c / 4), BnStats{u.R, u.acc, M, c, rows});
+    run(c, BnFinalize{u.acc, u.mean, u.invstd, u.rmean.p, u.rvar.p, M, c});
     const float* skip = u.skip_from >= 0 ? units[u.skip_from].A : nullptr;
     run(M * (c / 4), BnApply{u.R, u.mean, u.invstd, u.gamma.p, u.beta.p, skip, u.A, c, u.relu6});
   }
@@ -292,6 +305,11 @@ struct TrainerT {
     if (kind == 0) run(B, DimNllStep{dp, Z, target, scratch, gZ, loss_acc, B, T});
     else run(B, CilL1Step{dp, Z, target, scratch, gZ, pred_out, loss_acc, B, T});
     run(1, LossFinalize{loss_acc, loss, B});
+    const int64_t records = (int64_t)B * T;
+    run(192 * 64, DecGradWhh{scratch, whh.g, records});
+    run(192 * 4, DecGradIh{scratch, wih.g, bih.g, bhh.g, records, kind == 0 ? kRecMisc + 6 : kRecMisc});
+    if (kind == 0) run(32 * 65 + 4 * 33, DecGradHead{scratch, h1w.g, h1b.g, h2w.g, h2b.g, records, 32, 4, kRecDa1});
+    else run(2 * 65, DecGradHead{scratch, h1w.g, h1b.g, nullptr, nullptr, records, 2, 0, kRecDout});
 
     // ---- merger + classifier backward
     run(64 * (64 + 1), LinearBwdW{gZ, Z, H2, mg_w[2].g, mg_b[2].g, B, 64, 64, 64, 64, 1});
@@ -309,22 +327,28 @@ struct TrainerT {
       Unit& u = units[i];
       const int64_t M = (int64_t)B * u.hout * u.hout;
       const int c = u.cout;
-      run(chunks(M, kStatRows) * (c / 4),
-          BnBwdReduce{u.R, u.G, u.mean, u.invstd, u.gamma.p, u.beta.p, u.acc, M, c, u.relu6});
+      const int srows = pick_rows(M, c / 4, 16, 128);
+      run(chunks(M, srows) * (c / 4),
+          BnBwdReduce{u.R, u.G, u.mean, u.invstd, u.gamma.p, u.beta.p, u.acc, M, c, u.relu6, srows});
       run(c, BnBwdParams{u.acc, u.gamma.g, u.beta.g, u.mdp, u.mdpxh, M, c});
       float* gskip = u.skip_from >= 0 ? units[u.skip_from].G : nullptr;
       run(M * (c / 4), BnBwdDx{u.R, u.G, u.mean, u.invstd, u.gamma.p, u.beta.p, u.mdp, u.mdpxh, gskip, c, u.relu6});
       if (u.type == kStem) {
-        run(chunks(M, kStatRows) * 32 * (C * 9), StemBwdW{visual, u.G, u.w.g, B, C, u.hin, u.hin, u.hout, u.hout});
+        const int rows = pick_rows(M, 32, 16, 256);
+        run(chunks(M, rows) * 32, StemBwdW{visual, u.G, wrep, B, C, u.hin, u.hin, u.hout, u.hout, rows});
+        run(32 * C * 9, ReduceReplicas{wrep, u.w.g, 32 * C * 9});
         continue;
       }
       Unit& src = units[i - 1];
       if (u.type == kPointwise) {
-        run(chunks(M, kGradRows) * (u.cout / 4) * (u.cin / 4), PwBwdW{u.G, src.A, u.w.g, M, u.cout, u.cin});
+        const int rows = pick_rows(M, (int64_t)(u.cout / 4) * (u.cin / 4), 8, 256);
+        run(chunks(M, rows) * (u.cout / 4) * (u.cin / 4), PwBwdW{u.G, src.A, u.w.g, M, u.cout, u.cin, rows});
         run(chunks(M, 4) * (u.cin / 4), PwBwdX{u.G, u.w.p, src.G, M, u.cout, u.cin, u.input_has_skip});
       } else {
         const int64_t Min = (int64_t)B * u.hin * u.hin;
-        run(chunks(M, kStatRows) * (c / 4), DwBwdW{u.G, src.A, u.w.g, B, u.hin, u.hin, u.hout, u.hout, c, u.stride});
+        const int rows = pick_rows(M, c / 4, 16, 128);
+        run(chunks(M, rows) * (c / 4), DwBwdW{u.G, src.A, wrep, B, u.hin, u.hin, u.hout, u.hout, c, u.stride, rows});
+        run(c * 9, ReduceReplicas{wrep, u.w.g, c * 9});
         run(Min * (c / 4), DwBwdX{u.G, u.w.p, src.G, B, u.hin, u.hin, u.hout, u.hout, c, u.stride});
       }
     }
