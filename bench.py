@@ -328,7 +328,7 @@ def run_gpu_arm(args):
     if os.path.exists(tpath):  # dram bytes/launch from the last `ncu --set full` capture
       traffic = json.load(open(tpath)).get("flow_tc_kernel_pair_bytes")
     roofline = {
-        "kernel": "oat::flow_tc_kernel<0> + <1> (sample + score launches of one step)",
+        "kernel": "oat::flow_tc2_kernel<0> + <1> (sample + score launches of one step)",
         "bound": "tensor", "achieved": flow_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
         "frac": flow_tflops / tensor_peak, "traffic": traffic,
         "peak_source": peaks["source"] + ", bf16 dense sustained",
