@@ -78,6 +78,14 @@ OAT_API int oat_ensemble_reserve(OatEnsemble* ens, int32_t batch);
  * 0 = FP32 SIMT GEMM.  Both meet the 1e-4 parity bar; see DESIGN.md. */
 OAT_API int oat_ensemble_set_pw_impl(OatEnsemble* ens, int32_t impl);
 
+/* Selects which of the encoder's first blocks run as fused kernels (fused.cu): bit 0 =
+ * features.0 + features.1 (stem, depthwise, project) in one kernel; bits 1..3 = expand 1x1 +
+ * depthwise 3x3 of features.2 / .3 / .4 in one kernel, the 6x expanded tensor staying in
+ * shared memory.  Plain FP32 FMA arithmetic; results agree with the unfused path to
+ * rounding.  Default: OAT_FUSE_DEFAULT, or the environment variable OAT_FUSE.        */
+OAT_API int oat_ensemble_set_fusion(OatEnsemble* ens, int32_t mask);
+OAT_API int oat_ensemble_get_fusion(const OatEnsemble* ens);
+
 /* Selects the flow kernel family process-wide: 1 = tcgen05 3xTF32 recurrent GEMMs
  * with the state resident in shared/tensor memory (default), 0 = FP32 SIMT.        */
 OAT_API int oat_set_flow_impl(int32_t impl);
@@ -169,6 +177,12 @@ OAT_API int oat_cil_rollout(const OatModel* model, const float* z, int32_t B, in
 OAT_API int oat_debug_tc_gemm(const float* A, const float* W, const float* bias, const float* R,
                       float* C, int32_t M, int32_t K, int32_t N, int32_t E, int32_t relu6,
                       void* stream);
+
+/* TEST HOOK (tests/test_gpu_fused.py): the encoder up to and including `blocks`
+ * inverted-residual blocks (0 = the stem alone; with fusion bit 0 set the first available
+ * prefix is blocks = 1): visual [B,C,100,100] -> out [E][B][h][h][c] (NHWC).         */
+OAT_API int oat_debug_encoder_prefix(OatEnsemble* ens, const float* visual, int32_t B,
+                                     int32_t blocks, float* out, void* stream);
 
 /* ---- training step ----------------------------------------
  * A named DEVICE tensor of a model that is being trained: `param` points at the

@@ -26,6 +26,7 @@ SYMBOLS = (
     "oat_set_flow_impl", "oat_plan", "oat_plan_workspace_floats", "oat_goal_likelihood",
     "oat_transform_visual_hwc", "oat_lidar_bev", "oat_trainer_create", "oat_trainer_destroy",
     "oat_train_forward_backward", "oat_adam_step", "oat_trainer_activation",
+    "oat_ensemble_set_fusion", "oat_ensemble_get_fusion", "oat_debug_encoder_prefix",
 )
 
 
@@ -83,6 +84,9 @@ def lib() -> ctypes.CDLL:
                                     vp]
     L.oat_cil_rollout.argtypes = [vp, vp, c_i32, c_i32, vp, vp]
     L.oat_ensemble_set_pw_impl.argtypes = [vp, c_i32]
+    L.oat_ensemble_set_fusion.argtypes = [vp, c_i32]
+    L.oat_ensemble_get_fusion.argtypes = [vp]
+    L.oat_debug_encoder_prefix.argtypes = [vp, vp, c_i32, c_i32, vp, vp]
     L.oat_set_flow_impl.argtypes = [c_i32]
     L.oat_plan.argtypes = [ctypes.POINTER(vp), c_i32, c_i32, vp, vp, c_i32, c_f, c_i32, c_i32, c_i32,
                            c_f, vp, vp, vp, vp, c_i64, vp, vp]
@@ -123,6 +127,18 @@ def set_default_pw_impl(impl: str) -> None:
   global _default_pw_impl
   assert impl in ("tcgen05", "simt")
   _default_pw_impl = impl
+
+
+_default_fusion = None  # None: the library's default (OAT_FUSE_DEFAULT / env OAT_FUSE)
+
+
+def set_default_fusion(mask) -> None:
+  """Fusion mask (see `oat_ensemble_set_fusion`) for ensembles created from now on;
+  None restores the library default."""
+  global _default_fusion
+  if mask is not None and not 0 <= int(mask) <= 15:
+    raise ValueError("fusion mask must be in [0, 15]")
+  _default_fusion = None if mask is None else int(mask)
 
 
 def set_flow_impl(impl: str) -> None:
@@ -204,6 +220,8 @@ class EnsembleHandle:
     self.device = models[0].device
     if _default_pw_impl != "tcgen05":
       self.set_pw_impl(_default_pw_impl)
+    if _default_fusion is not None:
+      self.set_fusion(_default_fusion)
 
   def __len__(self):
     return len(self.models)
@@ -211,6 +229,13 @@ class EnsembleHandle:
   def set_pw_impl(self, impl: str) -> None:
     """"tcgen05" (3xTF32 tensor-core GEMMs, default) or "simt" (FP32 FFMA GEMMs)."""
     check(lib().oat_ensemble_set_pw_impl(self.ptr, {"simt": 0, "tcgen05": 1}[impl]))
+
+  def set_fusion(self, mask: int) -> None:
+    """Bit 0: features.0+1 as one kernel; bits 1-3: expand+depthwise of features.2-4 fused."""
+    check(lib().oat_ensemble_set_fusion(self.ptr, int(mask)))
+
+  def fusion(self) -> int:
+    return int(lib().oat_ensemble_get_fusion(self.ptr))
 
   def __deepcopy__(self, memo):
     return None

@@ -6,6 +6,7 @@
 // precision), transposes every matrix into the K-major layout the kernels read
 // and uploads one arena per model.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -342,6 +343,11 @@ int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble
     e->models.push_back(models[i]);
   }
   e->device = models[0]->device;
+#ifndef OAT_FUSE_DEFAULT
+#define OAT_FUSE_DEFAULT 0
+#endif
+  e->fuse = OAT_FUSE_DEFAULT;
+  if (const char* env = getenv("OAT_FUSE")) e->fuse = atoi(env) & 15;
   // ---- tensor-core copies of every pointwise layer: [E][N][K], TF32 hi/lo split ----
   {
     const OatModel* m0 = models[0];
@@ -410,6 +416,15 @@ int oat_ensemble_set_pw_impl(OatEnsemble* ens, int32_t impl) {
   ens->pw_impl = impl;
   return 0;
 }
+
+int oat_ensemble_set_fusion(OatEnsemble* ens, int32_t mask) {
+  if (!ens) return fail("oat_ensemble_set_fusion: null ensemble");
+  if (mask < 0 || mask > 15) return fail("oat_ensemble_set_fusion: mask must be in [0, 15]");
+  ens->fuse = mask;
+  return 0;
+}
+
+int oat_ensemble_get_fusion(const OatEnsemble* ens) { return ens ? ens->fuse : -1; }
 
 int oat_debug_tc_gemm(const float* A, const float* W, const float* bias, const float* R, float* C,
                       int32_t M, int32_t K, int32_t N, int32_t E, int32_t relu6, void* stream) {
@@ -501,6 +516,18 @@ int oat_encode(OatEnsemble* ens, const float* visual, const float* scalars, int3
   if (int rc = check_device(ens->device, "oat_encode")) return rc;
   if (int rc = oat_ensemble_reserve(ens, B)) return rc;
   return encoder_forward(ens, visual, scalars, B, z, (cudaStream_t)stream);
+}
+
+int oat_debug_encoder_prefix(OatEnsemble* ens, const float* visual, int32_t B, int32_t blocks,
+                             float* out, void* stream) {
+  if (B <= 0) return 0;
+  if (!ens || !visual || !out) return fail("oat_debug_encoder_prefix: null argument");
+  if (blocks < 0 || blocks > 17) return fail("oat_debug_encoder_prefix: blocks must be in [0, 17]");
+  if (blocks == 0 && (ens->fuse & 1))
+    return fail("oat_debug_encoder_prefix: the fused front has no stem-only output");
+  if (int rc = check_device(ens->device, "oat_debug_encoder_prefix")) return rc;
+  if (int rc = oat_ensemble_reserve(ens, B)) return rc;
+  return encoder_forward(ens, visual, nullptr, B, nullptr, (cudaStream_t)stream, blocks, out);
 }
 
 static PtrTable one_model(const OatModel* m) {

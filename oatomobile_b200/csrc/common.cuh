@@ -103,6 +103,8 @@ struct OatEnsemble {
   std::vector<oat::TcLayer> tc;  // pointwise layers in execution order (+ last, fc)
   float* tc_arena = nullptr;
   int pw_impl = 1;               // 1 = tcgen05 3xTF32 (default), 0 = FP32 SIMT
+  int fuse = 0;                  // bit 0: features.0+1 in one kernel; bits 1-3: expand+depthwise
+                                 // of features.2-4 in one kernel (fused.cu)
   int device = 0;
   int reserved_batch = 0;
   float* ws = nullptr;  // activation workspace
@@ -176,7 +178,11 @@ int launch_aggregate(const float* q, int E, int B, int K, int algo, const float*
 int launch_transform_visual(const float* lidar, int B, int C, int H, int W, float* visual,
                             cudaStream_t stream, bool hwc = false);
 
+// stop_after_blocks >= 0 (debug): stop after that many inverted-residual blocks (0 = after the
+// stem, unless the fused front already contains block 1) and copy the activation
+// [E][B][h][h][c] to prefix_out.
 int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars, int B,
-                    float* z, cudaStream_t stream);
+                    float* z, cudaStream_t stream, int stop_after_blocks = -1,
+                    float* prefix_out = nullptr);
 
 }  // namespace oat

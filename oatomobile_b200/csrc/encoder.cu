@@ -10,6 +10,7 @@
 // pointwise convolutions are [M=B*H*W, K] x [K, N] GEMMs with a fused
 // bias(+BN) / ReLU6 / residual epilogue.
 #include "common.cuh"
+#include "fused.cuh"
 #include "tc_gemm.cuh"
 
 namespace oat {
@@ -525,7 +526,7 @@ int launch_transform_visual(const float* lidar, int B, int C, int H, int W, floa
 }
 
 int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars, int B,
-                    float* z, cudaStream_t stream) {
+                    float* z, cudaStream_t stream, int stop_after_blocks, float* prefix_out) {
   const int E = (int)ens->models.size();
   const OatModel* m0 = ens->models[0];
   const int C = m0->in_channels;
@@ -537,8 +538,25 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
     return t;
   };
 
-  // stem -> bufA [E][B][50][50][32]
-  {
+  float* x = ens->bufA;
+  float* y = ens->bufB;
+  size_t li = 0;  // index into ens->tc (pointwise layers in execution order)
+  size_t first_block = 0;
+  if (ens->fuse & 1) {
+    // features.0 + features.1 in one kernel (fused.cu): visual -> bufA [E][B][50][50][16]
+    FusedFrontLaunch f;
+    f.ws = table([](const OatModel* m) { return m->stem.w; });
+    f.bs = table([](const OatModel* m) { return m->stem.b; });
+    f.wd = table([](const OatModel* m) { return m->blocks[0].dw.w; });
+    f.bd = table([](const OatModel* m) { return m->blocks[0].dw.b; });
+    f.wp = table([](const OatModel* m) { return m->blocks[0].project.w; });
+    f.bp = table([](const OatModel* m) { return m->blocks[0].project.b; });
+    f.visual = visual; f.out = x; f.E = E; f.B = B; f.C = C;
+    if (int rc = launch_fused_front(f, stream)) return rc;
+    first_block = 1;
+    li = 1;  // the project layer of block 1
+  } else {
+    // stem -> bufA [E][B][50][50][32]
     PtrTable w = table([](const OatModel* m) { return m->stem.w; });
     PtrTable b = table([](const OatModel* m) { return m->stem.b; });
 #if !defined(OAT_STEM_1PX)
@@ -549,19 +567,39 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
     stem_kernel<<<grid, STEM_THREADS, 0, stream>>>(w, b, visual, B, C, ens->bufA);
     OAT_LAUNCH_CHECK();
   }
-  float* x = ens->bufA;
-  float* y = ens->bufB;
-  size_t li = 0;  // index into ens->tc (pointwise layers in execution order)
+  auto prefix_done = [&](size_t blocks_done, const float* act, int h, int c) -> int {
+    if (stop_after_blocks < 0 || (size_t)stop_after_blocks != blocks_done) return 0;
+    OAT_CUDA(cudaMemcpyAsync(prefix_out, act, (size_t)E * B * h * h * c * sizeof(float),
+                             cudaMemcpyDeviceToDevice, stream));
+    return -1;
+  };
+  if (first_block == 1) {
+    if (int rc = prefix_done(1, x, 50, 16)) return rc < 0 ? 0 : rc;
+  } else {
+    if (int rc = prefix_done(0, x, 50, 32)) return rc < 0 ? 0 : rc;
+  }
   auto tc = [&]() -> const TcLayer* {
     const TcLayer* t = ens->pw_impl == 1 ? &ens->tc[li] : nullptr;
     ++li;
     return t;
   };
-  for (size_t bi = 0; bi < m0->blocks.size(); ++bi) {
+  for (size_t bi = first_block; bi < m0->blocks.size(); ++bi) {
     const BlockW& blk = m0->blocks[bi];
     const int Min = B * blk.hin * blk.hin, Mout = B * blk.hout * blk.hout;
     const float* dw_in = x;
-    if (blk.hid != blk.cin) {  // expand 1x1 + BN + ReLU6
+    const bool fuse_block = bi >= 1 && bi <= 3 && ((ens->fuse >> bi) & 1) &&
+                            fused_block_supported(blk.cin, blk.hid, blk.stride, blk.hin);
+    if (fuse_block) {  // expand + depthwise in one kernel: the 6x tensor stays in shared memory
+      FusedBlockLaunch f;
+      f.we = table([bi](const OatModel* m) { return m->blocks[bi].expand.w; });
+      f.be = table([bi](const OatModel* m) { return m->blocks[bi].expand.b; });
+      f.wd = table([bi](const OatModel* m) { return m->blocks[bi].dw.w; });
+      f.bd = table([bi](const OatModel* m) { return m->blocks[bi].dw.b; });
+      f.in = x; f.out = ens->bufH2; f.E = E; f.B = B;
+      f.cin = blk.cin; f.hid = blk.hid; f.stride = blk.stride; f.hin = blk.hin;
+      if (int rc = launch_fused_expand_dw(f, stream)) return rc;
+      ++li;  // the expand layer's tensor-core copy is not used
+    } else if (blk.hid != blk.cin) {  // expand 1x1 + BN + ReLU6
       PwArgs a;
       a.w = table([bi](const OatModel* m) { return m->blocks[bi].expand.w; });
       a.bias = table([bi](const OatModel* m) { return m->blocks[bi].expand.b; });
@@ -571,7 +609,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       if (int rc = launch_pw(a, E, stream, tc())) return rc;
       dw_in = ens->bufH1;
     }
-    {  // depthwise 3x3 + BN + ReLU6
+    if (!fuse_block) {  // depthwise 3x3 + BN + ReLU6
       PtrTable w = table([bi](const OatModel* m) { return m->blocks[bi].dw.w; });
       PtrTable b = table([bi](const OatModel* m) { return m->blocks[bi].dw.b; });
       const int64_t total = (int64_t)B * blk.hout * (blk.hid / 4);
@@ -600,6 +638,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       if (int rc = launch_pw(a, E, stream, tc())) return rc;
     }
     float* t = x; x = y; y = t;
+    if (int rc = prefix_done(bi + 1, x, blk.hout, blk.cout)) return rc < 0 ? 0 : rc;
   }
   const int hl = m0->blocks.back().hout;  // 4
   const int P = hl * hl;

@@ -1,0 +1,437 @@
+// Fused front of the BEV encoder: CTA bodies that keep the wide intermediate tensors of
+// MobileNetV2's first blocks in shared memory instead of HBM.
+//
+//   FrontBody      features.0 (3x3 s2 conv C->32 + BN + ReLU6) -> features.1 depthwise 3x3
+//                  (+BN+ReLU6) -> features.1 project 32->16 (+BN)       [perception.py:43-55]
+//   ExpandDwBody   expand 1x1 (cin -> 6 cin, +BN+ReLU6) -> depthwise 3x3 (stride 1|2,
+//                  +BN+ReLU6) of one inverted-residual block; the 6x expanded tensor lives
+//                  only as a ring of a few image rows in shared memory.  The project 1x1
+//                  stays on the tcgen05 GEMM (tc_gemm.cu).
+//
+// Both walk an image top to bottom.  Per iteration: stage the next input rows (cp.async,
+// double-buffered, issued one iteration ahead), run the pointwise convolution of the new
+// rows as a register-tiled FP32 GEMM out of shared memory into the row ring, then slide the
+// 3x3 depthwise window over the ring.  BatchNorms are folded at pack time (api.cu).
+//
+// A body is written against an executor `X` that provides shared memory, `phase(f)` =
+// "run f(tid) for every thread, then barrier", and 16-byte asynchronous copies.  fused.cu
+// instantiates it with the CUDA executor (the product); tests/emu instantiates it with a
+// host loop so the `-m "not gpu"` suite can check the tiling, ring and padding logic
+// against the oracle without a GPU (test tooling, never loaded by the package).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define OAT_FHD __host__ __device__ __forceinline__
+#define OAT_FUNROLL _Pragma("unroll")
+#else
+#define OAT_FHD inline
+#define OAT_FUNROLL
+#endif
+
+namespace oat {
+namespace fused {
+
+constexpr int kMaxModels = 16;
+
+struct alignas(16) F4 {
+  float x, y, z, w;
+};
+OAT_FHD F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
+OAT_FHD void st4(float* p, F4 v) { *reinterpret_cast<F4*>(p) = v; }
+OAT_FHD F4 zero4() { return F4{0.0f, 0.0f, 0.0f, 0.0f}; }
+OAT_FHD float relu6f(float v) { return fminf(fmaxf(v, 0.0f), 6.0f); }
+OAT_FHD F4 relu6_4(F4 v) { return F4{relu6f(v.x), relu6f(v.y), relu6f(v.z), relu6f(v.w)}; }
+OAT_FHD F4 fma4(F4 a, F4 b, F4 c) {
+  return F4{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w)};
+}
+OAT_FHD float gload(const float* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+OAT_FHD F4 gload4(const float* p) {
+#if defined(__CUDA_ARCH__)
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  return F4{v.x, v.y, v.z, v.w};
+#else
+  return ld4(p);
+#endif
+}
+OAT_FHD void gstore4(float* p, F4 v) {
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<float4*>(p) = make_float4(v.x, v.y, v.z, v.w);
+#else
+  st4(p, v);
+#endif
+}
+
+struct Weights {  // per-model device pointers, passed by value
+  const float* p[kMaxModels];
+};
+
+// ---------------------------------------------------------------------------------------
+// out(p, c4) = bias[c4] + sum_k A[p][k] * W[k][c4]   for rows p < P, 4-channel groups c4 < N4.
+// A: shared memory, row stride lda floats (lda % 8 == 4: conflict-free 16-byte row reads);
+// W: shared memory [K][ldw]; K % 4 == 0.  Work item = (row group, c4), c4 fastest: the
+// lanes of a warp read consecutive weight float4s and mostly one A row (broadcast).  A
+// thread owns TP rows pg, pg+PG, pg+2PG, ... so every weight float4 feeds 4*TP FMAs.
+// ---------------------------------------------------------------------------------------
+template <int TP, class Emit>
+OAT_FHD void gemm_rows(const float* A, int lda, const float* W, int ldw, const float* bias,
+                       int P, int K, int N4, int tid, int nthreads, Emit emit) {
+  const int PG = (P + TP - 1) / TP;
+  for (int item = tid; item < PG * N4; item += nthreads) {
+    const int pg = item / N4, c4 = item - pg * N4;
+    const F4 b = ld4(bias + 4 * c4);
+    F4 acc[TP];
+    const float* ap[TP];
+    OAT_FUNROLL
+    for (int j = 0; j < TP; ++j) {
+      acc[j] = b;
+      const int p = pg + j * PG;
+      ap[j] = A + (p < P ? p : P - 1) * lda;  // tail rows recompute the last row, never stored
+    }
+    const float* wp = W + 4 * c4;
+    for (int k = 0; k < K; k += 4) {
+      const F4 w0 = ld4(wp + (k + 0) * ldw), w1 = ld4(wp + (k + 1) * ldw);
+      const F4 w2 = ld4(wp + (k + 2) * ldw), w3 = ld4(wp + (k + 3) * ldw);
+      OAT_FUNROLL
+      for (int j = 0; j < TP; ++j) {
+        const F4 a = ld4(ap[j] + k);
+        F4 c = acc[j];
+        c.x = fmaf(a.x, w0.x, c.x); c.y = fmaf(a.x, w0.y, c.y); c.z = fmaf(a.x, w0.z, c.z); c.w = fmaf(a.x, w0.w, c.w);
+        c.x = fmaf(a.y, w1.x, c.x); c.y = fmaf(a.y, w1.y, c.y); c.z = fmaf(a.y, w1.z, c.z); c.w = fmaf(a.y, w1.w, c.w);
+        c.x = fmaf(a.z, w2.x, c.x); c.y = fmaf(a.z, w2.y, c.y); c.z = fmaf(a.z, w2.z, c.z); c.w = fmaf(a.z, w2.w, c.w);
+        c.x = fmaf(a.w, w3.x, c.x); c.y = fmaf(a.w, w3.y, c.y); c.z = fmaf(a.w, w3.z, c.z); c.w = fmaf(a.w, w3.w, c.w);
+        acc[j] = c;
+      }
+    }
+    OAT_FUNROLL
+    for (int j = 0; j < TP; ++j) {
+      const int p = pg + j * PG;
+      if (p < P) emit(p, c4, acc[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Depthwise 3x3 (pad 1, stride S) + bias + ReLU6 over a ring of NR = S*(OR-1)+3 image rows
+// in shared memory, producing OR output rows.  ring: [NR slots][win][ld] floats, the input
+// row `ir` sits in slot (ir mod NR); rows outside the image hold zeros (the caller fills
+// them), columns outside the image read as zeros here.  Work item = (column segment, c4),
+// c4 fastest; the 3-column window slides along the segment in registers.
+// wd: [9][hid] (tap-major), bd: [hid], both in shared memory.
+// emit(o, oc, c4, v): output row orow0 + o (o < OR), column oc.
+// ---------------------------------------------------------------------------------------
+template <int S, int OR, class Emit>
+OAT_FHD void dw_rows(const float* ring, int ld, int win, int wout, const float* wd, const float* bd,
+                     int hid, int ir0, int nseg, int tid, int nthreads, Emit emit) {
+  constexpr int NR = S * (OR - 1) + 3;
+  const int N4 = hid >> 2;
+  for (int item = tid; item < nseg * N4; item += nthreads) {
+    const int seg = item / N4, c4 = item - seg * N4;
+    const int c_lo = (seg * wout) / nseg, c_hi = ((seg + 1) * wout) / nseg;
+    if (c_lo >= c_hi) continue;
+    F4 k[9];
+    OAT_FUNROLL
+    for (int t = 0; t < 9; ++t) k[t] = ld4(wd + t * hid + 4 * c4);
+    const F4 bv = ld4(bd + 4 * c4);
+    const float* rowp[NR];
+    OAT_FUNROLL
+    for (int r = 0; r < NR; ++r) {
+      const int slot = ((ir0 + r) % NR + NR) % NR;
+      rowp[r] = ring + (slot * win) * ld + 4 * c4;
+    }
+    F4 c0[NR], c1[NR], c2[NR];
+    auto ldcol = [&](int ic, F4(&col)[NR]) {
+      const bool ok = ic >= 0 && ic < win;
+      OAT_FUNROLL
+      for (int r = 0; r < NR; ++r) col[r] = ok ? ld4(rowp[r] + ic * ld) : zero4();
+    };
+    ldcol(S * c_lo - 1, c0);
+    ldcol(S * c_lo, c1);
+    for (int oc = c_lo; oc < c_hi; ++oc) {
+      ldcol(S * oc + 1, c2);
+      OAT_FUNROLL
+      for (int o = 0; o < OR; ++o) {
+        F4 acc = bv;
+        OAT_FUNROLL
+        for (int kh = 0; kh < 3; ++kh) {
+          acc = fma4(c0[S * o + kh], k[3 * kh + 0], acc);
+          acc = fma4(c1[S * o + kh], k[3 * kh + 1], acc);
+          acc = fma4(c2[S * o + kh], k[3 * kh + 2], acc);
+        }
+        emit(o, oc, c4, relu6_4(acc));
+      }
+      if (S == 1) {
+        OAT_FUNROLL
+        for (int r = 0; r < NR; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
+      } else {
+        OAT_FUNROLL
+        for (int r = 0; r < NR; ++r) c0[r] = c2[r];
+        if (oc + 1 < c_hi) ldcol(S * (oc + 1), c1);
+      }
+    }
+  }
+}
+
+// =======================================================================================
+// ExpandDwBody<CIN, HID, S, HIN, OR, TP, NSEG>
+//   in  [E][B][HIN][HIN][CIN]  (NHWC, output of the previous block)
+//   out [E][B][HOUT][HOUT][HID] = relu6(dw3x3_S(relu6(in W_e + b_e)) + b_d)
+// CTA = (model, image, split): `splits` CTAs share an image, each walks a contiguous range
+// of output-row groups (OR rows per group) top to bottom.
+// =======================================================================================
+struct ExpandDwArgs {
+  Weights we, be, wd, bd;  // expand [CIN][HID] + [HID]; depthwise [9][HID] + [HID]
+  const float* in;
+  float* out;
+  int B;       // images per model
+  int splits;  // CTAs per image
+};
+
+template <int CIN_, int HID_, int S_, int HIN_, int OR_, int TP_, int NSEG_>
+struct ExpandDwBody {
+  static constexpr int CIN = CIN_, HID = HID_, S = S_, HIN = HIN_, OR = OR_, TP = TP_, NSEG = NSEG_;
+  static constexpr int HOUT = (HIN - 1) / S + 1;
+  static constexpr int NR = S * (OR - 1) + 3;   // ring rows
+  static constexpr int NEW = S * OR;            // new input rows per iteration
+  static constexpr int PRIME = NR - NEW;        // rows of the priming pass (3 - S)
+  static constexpr int LDX = CIN + 4;           // staged input pixel stride
+  static constexpr int LDE = HID + 4;           // ring pixel stride
+  static constexpr int GROUPS = (HOUT + OR - 1) / OR;
+  static_assert(PRIME >= 1 && PRIME <= NEW, "stride 1 needs OR >= 2");
+  static_assert(CIN % 4 == 0 && HID % 4 == 0, "channel counts must be multiples of 4");
+  // shared-memory map (floats)
+  static constexpr int kWe = 0;
+  static constexpr int kBe = kWe + CIN * HID;
+  static constexpr int kWd = kBe + HID;
+  static constexpr int kBd = kWd + 9 * HID;
+  static constexpr int kX = kBd + HID;                    // 2 staging buffers
+  static constexpr int kXFloats = NEW * HIN * LDX;
+  static constexpr int kRing = kX + 2 * kXFloats;
+  static constexpr int kSmemFloats = kRing + NR * HIN * LDE;
+
+  template <class X>
+  OAT_FHD static void run(X& x, const ExpandDwArgs& a, int cta) {
+    float* sm = x.smem();
+    const int nt = x.nthreads();
+    const int split = cta % a.splits;
+    const int img = cta / a.splits;  // model * B + b
+    const int model = img / a.B;
+    const float* in = a.in + (int64_t)img * HIN * HIN * CIN;
+    float* out = a.out + (int64_t)img * HOUT * HOUT * HID;
+    const int g0 = (split * GROUPS) / a.splits, g1 = ((split + 1) * GROUPS) / a.splits;
+    if (g0 >= g1) return;
+    float* We = sm + kWe;
+    float* Be = sm + kBe;
+    float* Wd = sm + kWd;
+    float* Bd = sm + kBd;
+    float* ring = sm + kRing;
+
+    // input rows [lo, lo+n) clipped to the image -> staging buffer `buf` (pixel-major, LDX)
+    auto stage = [&](int tid, int buf, int lo, int n) {
+      const int vlo = lo < 0 ? 0 : lo;
+      const int vhi = lo + n > HIN ? HIN : lo + n;
+      if (vhi <= vlo) return;
+      float* dst = sm + kX + buf * kXFloats;
+      const float* src = in + (int64_t)vlo * HIN * CIN;
+      const int chunks = (vhi - vlo) * HIN * (CIN / 4);
+      for (int i = tid; i < chunks; i += nt) {
+        const int px = i / (CIN / 4), q = i - px * (CIN / 4);
+        x.async16(dst + px * LDX + 4 * q, src + px * CIN + 4 * q);
+      }
+    };
+    // expand rows [lo, lo+n) from staging buffer `buf` into the ring (zeros outside the image)
+    auto expand = [&](int tid, int buf, int lo, int n) {
+      const int vlo = lo < 0 ? 0 : lo;
+      const int vhi = lo + n > HIN ? HIN : lo + n;
+      for (int ir = lo; ir < lo + n; ++ir) {
+        if (ir >= 0 && ir < HIN) continue;
+        float* row = ring + (((ir % NR) + NR) % NR) * HIN * LDE;
+        for (int i = tid; i < HIN * LDE / 4; i += nt) st4(row + 4 * i, zero4());
+      }
+      if (vhi <= vlo) return;
+      const float* Xs = sm + kX + buf * kXFloats;
+      gemm_rows<TP>(Xs, LDX, We, HID, Be, (vhi - vlo) * HIN, CIN, HID / 4, tid, nt,
+                    [&](int p, int c4, F4 v) {
+                      const int r = p / HIN, col = p - r * HIN;
+                      const int slot = (vlo + r) % NR;
+                      st4(ring + (slot * HIN + col) * LDE + 4 * c4, relu6_4(v));
+                    });
+    };
+
+    const int ir_first = S * g0 * OR - 1;  // first ring row of the first group
+    x.phase([&](int tid) {
+      const float *we = a.we.p[model], *be = a.be.p[model], *wd = a.wd.p[model], *bd = a.bd.p[model];
+      for (int i = tid; i < CIN * HID / 4; i += nt) st4(We + 4 * i, gload4(we + 4 * i));
+      for (int i = tid; i < HID / 4; i += nt) st4(Be + 4 * i, gload4(be + 4 * i));
+      for (int i = tid; i < 9 * HID / 4; i += nt) st4(Wd + 4 * i, gload4(wd + 4 * i));
+      for (int i = tid; i < HID / 4; i += nt) st4(Bd + 4 * i, gload4(bd + 4 * i));
+      stage(tid, 0, ir_first, PRIME);
+      stage(tid, 1, ir_first + PRIME, NEW);
+      x.async_wait();
+    });
+    x.phase([&](int tid) { expand(tid, 0, ir_first, PRIME); });
+    for (int g = g0; g < g1; ++g) {
+      const int buf = (g - g0 + 1) & 1;
+      const int ir0 = S * g * OR - 1;
+      x.phase([&](int tid) {
+        if (g + 1 < g1) stage(tid, buf ^ 1, ir0 + NEW + PRIME, NEW);  // rows of group g+1
+        expand(tid, buf, ir0 + PRIME, NEW);
+      });
+      x.phase([&](int tid) {
+        dw_rows<S, OR>(ring, LDE, HIN, HOUT, Wd, Bd, HID, ir0, NSEG, tid, nt,
+                       [&](int o, int oc, int c4, F4 v) {
+                         const int orow = g * OR + o;
+                         if (orow < HOUT) gstore4(out + ((int64_t)orow * HOUT + oc) * HID + 4 * c4, v);
+                       });
+        x.async_wait();
+      });
+    }
+  }
+};
+
+// =======================================================================================
+// FrontBody: visual NCHW [B][C][100][100] (shared by the models) ->
+//            out [E][B][50][50][16] = features.1(features.0(visual))
+// =======================================================================================
+struct FrontArgs {
+  Weights ws, bs;  // stem [9*C][32] (k = (kh*3+kw)*C + c) + [32]
+  Weights wd, bd;  // features.1 depthwise [9][32] + [32]
+  Weights wp, bp;  // features.1 project [32][16] + [16]
+  const float* vis;
+  float* out;
+  int B, C, splits;
+};
+
+struct FrontBody {
+  static constexpr int HI = 100, HS = 50;      // input / stem-output size
+  static constexpr int NR = 4, NEW = 2;        // ring rows, new stem rows per iteration
+  static constexpr int XR = 2 * NEW + 1;       // input rows staged per iteration
+  static constexpr int LDS_ = 36;              // ring / depthwise-output pixel stride (32 + 4)
+  static constexpr int PAIRS = HS / 2;
+  OAT_FHD static int kp(int C) { return (9 * C + 3) & ~3; }   // im2col depth, padded
+  OAT_FHD static int ldi(int C) { return kp(C) + 4; }
+  // shared-memory map (floats)
+  OAT_FHD static int oWs(int) { return 0; }
+  OAT_FHD static int oBs(int C) { return kp(C) * 32; }
+  OAT_FHD static int oWd(int C) { return oBs(C) + 32; }
+  OAT_FHD static int oBd(int C) { return oWd(C) + 9 * 32; }
+  OAT_FHD static int oWp(int C) { return oBd(C) + 32; }
+  OAT_FHD static int oBp(int C) { return oWp(C) + 32 * 16; }
+  OAT_FHD static int oXI(int C) { return oBp(C) + 16; }                   // 2 x [C][XR][100]
+  OAT_FHD static int oIM(int C) { return oXI(C) + 2 * C * XR * HI; }      // [NEW*50][ldi]
+  OAT_FHD static int oRing(int C) { return oIM(C) + NEW * HS * ldi(C); }  // [NR][50][36]
+  OAT_FHD static int oD(int C) { return oRing(C) + NR * HS * LDS_; }      // [2*50][36]
+  OAT_FHD static int smem_floats(int C) { return oD(C) + 2 * HS * LDS_; }
+
+  template <class X>
+  OAT_FHD static void run(X& x, const FrontArgs& a, int cta) {
+    float* sm = x.smem();
+    const int nt = x.nthreads();
+    const int C = a.C, KP = kp(C), LDI = ldi(C);
+    const int split = cta % a.splits;
+    const int img = cta / a.splits;  // model * B + b
+    const int model = img / a.B, b = img - model * a.B;
+    const float* vis = a.vis + (int64_t)b * C * HI * HI;
+    float* out = a.out + (int64_t)img * HS * HS * 16;
+    const int p0 = (split * PAIRS) / a.splits, p1 = ((split + 1) * PAIRS) / a.splits;
+    if (p0 >= p1) return;
+    float* Ws = sm + oWs(C);
+    float* Bs = sm + oBs(C);
+    float* Wd = sm + oWd(C);
+    float* Bd = sm + oBd(C);
+    float* Wp = sm + oWp(C);
+    float* Bp = sm + oBp(C);
+    float* IM = sm + oIM(C);
+    float* ring = sm + oRing(C);
+    float* D = sm + oD(C);
+
+    // input rows 2*sr-1 .. 2*sr+3 of every channel for the stem rows [sr, sr+2)
+    auto stage = [&](int tid, int buf, int sr) {
+      float* dst = sm + oXI(C) + buf * C * XR * HI;
+      const int lo = 2 * sr - 1;
+      for (int i = tid; i < C * XR * (HI / 4); i += nt) {
+        const int q = i % (HI / 4), r = (i / (HI / 4)) % XR, c = i / ((HI / 4) * XR);
+        const int ir = lo + r;
+        if (ir < 0 || ir >= HI) continue;
+        x.async16(dst + (c * XR + r) * HI + 4 * q, vis + ((int64_t)c * HI + ir) * HI + 4 * q);
+      }
+    };
+    // im2col of the stem rows [sr, sr+2): IM[(r*50+ow)][(kh*3+kw)*C + c]
+    auto im2col = [&](int tid, int buf, int sr) {
+      const float* XI = sm + oXI(C) + buf * C * XR * HI;
+      for (int i = tid; i < NEW * HS * 9; i += nt) {
+        const int t = i % 9, p = i / 9;
+        const int kh = t / 3, kw = t - 3 * kh;
+        const int r = p / HS, ow = p - r * HS;
+        const int ir = 2 * (sr + r) - 1 + kh, ic = 2 * ow - 1 + kw;
+        const bool ok = ir >= 0 && ir < HI && ic >= 0 && ic < HI;
+        const int xr = 2 * r + kh;
+        float* dst = IM + p * LDI + t * C;
+        for (int c = 0; c < C; ++c) dst[c] = ok ? XI[(c * XR + xr) * HI + ic] : 0.0f;
+      }
+    };
+    // stem GEMM of the rows [sr, sr+2) into the ring (rows outside the image: zeros)
+    auto stem = [&](int tid, int sr) {
+      gemm_rows<4>(IM, LDI, Ws, 32, Bs, NEW * HS, KP, 8, tid, nt, [&](int p, int c4, F4 v) {
+        const int r = p / HS, ow = p - r * HS;
+        const int row = sr + r;
+        const bool ok = row >= 0 && row < HS;
+        const int slot = ((row % NR) + NR) % NR;
+        st4(ring + (slot * HS + ow) * LDS_ + 4 * c4, ok ? relu6_4(v) : zero4());
+      });
+    };
+
+    const int sr_first = 2 * p0 - 1;  // first ring row of the first output pair
+    x.phase([&](int tid) {
+      const float *ws = a.ws.p[model], *bs = a.bs.p[model], *wd = a.wd.p[model], *bd = a.bd.p[model];
+      const float *wp = a.wp.p[model], *bp = a.bp.p[model];
+      for (int i = tid; i < KP * 32; i += nt) Ws[i] = i < 9 * C * 32 ? gload(ws + i) : 0.0f;
+      for (int i = tid; i < 32; i += nt) { Bs[i] = gload(bs + i); Bd[i] = gload(bd + i); }
+      for (int i = tid; i < 9 * 32; i += nt) Wd[i] = gload(wd + i);
+      for (int i = tid; i < 32 * 16; i += nt) Wp[i] = gload(wp + i);
+      for (int i = tid; i < 16; i += nt) Bp[i] = gload(bp + i);
+      for (int i = tid; i < NEW * HS * LDI; i += nt) IM[i] = 0.0f;  // incl. the padded k columns
+      stage(tid, 0, sr_first);
+      x.async_wait();
+    });
+    // priming pass: stem rows sr_first, sr_first+1
+    x.phase([&](int tid) {
+      stage(tid, 1, sr_first + 2);
+      im2col(tid, 0, sr_first);
+    });
+    x.phase([&](int tid) {
+      stem(tid, sr_first);
+      x.async_wait();
+    });
+    for (int p = p0; p < p1; ++p) {
+      const int buf = (p - p0 + 1) & 1;
+      const int sr = 2 * p + 1;  // new stem rows sr, sr+1 complete the window 2p-1 .. 2p+2
+      x.phase([&](int tid) {
+        if (p + 1 < p1) stage(tid, buf ^ 1, sr + 2);
+        im2col(tid, buf, sr);
+      });
+      x.phase([&](int tid) { stem(tid, sr); });
+      x.phase([&](int tid) {
+        dw_rows<1, 2>(ring, LDS_, HS, HS, Wd, Bd, 32, 2 * p - 1, 16, tid, nt,
+                      [&](int o, int oc, int c4, F4 v) { st4(D + (o * HS + oc) * LDS_ + 4 * c4, v); });
+      });
+      x.phase([&](int tid) {
+        gemm_rows<2>(D, LDS_, Wp, 16, Bp, 2 * HS, 32, 4, tid, nt, [&](int q, int c4, F4 v) {
+          gstore4(out + ((int64_t)(2 * p) * HS + q) * 16 + 4 * c4, v);
+        });
+        x.async_wait();
+      });
+    }
+  }
+};
+
+}  // namespace fused
+}  // namespace oat

@@ -47,6 +47,24 @@ def encode(ens: N.EnsembleHandle, visual: torch.Tensor, scalars: torch.Tensor) -
   return z
 
 
+# (h, c) of the activation after `blocks` inverted-residual blocks (0 = stem)
+_PREFIX_SHAPES = [(50, 32), (50, 16), (25, 24), (25, 24), (13, 32), (13, 32), (13, 32), (7, 64),
+                  (7, 64), (7, 64), (7, 64), (7, 96), (7, 96), (7, 96), (4, 160), (4, 160),
+                  (4, 160), (4, 320)]
+
+
+def encoder_prefix(ens: N.EnsembleHandle, visual: torch.Tensor, blocks: int) -> torch.Tensor:
+  """TEST HOOK — the encoder's activation after `blocks` blocks: -> [E,B,h,h,c] (NHWC)."""
+  visual = N.require_cuda_f32(visual, "visual_features")
+  B = visual.shape[0]
+  h, c = _PREFIX_SHAPES[blocks]
+  out = torch.empty(len(ens), B, h, h, c, device=visual.device, dtype=torch.float32)
+  with torch.cuda.device(visual.device):
+    N.check(N.lib().oat_debug_encoder_prefix(ens.ptr, visual.data_ptr(), B, blocks, out.data_ptr(),
+                                             N.stream_ptr(visual.device)))
+  return out
+
+
 def flow_forward(model: N.ModelHandle, x: torch.Tensor, z: torch.Tensor,
                  rows_per_z: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
   """sequence.py:95-151 — x [N,T,2], z [N/rows_per_z,64] -> y, logabsdet."""

@@ -1,0 +1,85 @@
+// TEST TOOLING — host execution of the fused encoder-front CTA bodies.
+//
+// Compiles oatomobile_b200/csrc/fused_body.h (the exact code the CUDA product runs inside
+// fused.cu's kernels) with g++ and an executor whose "phase" is a plain loop over thread
+// ids and whose asynchronous copies complete immediately, so the `-m "not gpu"` tests can
+// check the tiling / ring / padding logic against the oracle without a GPU.  Never
+// imported, linked or loaded by the oatomobile_b200 package.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../oatomobile_b200/csrc/fused_body.h"
+
+namespace {
+
+using namespace oat::fused;
+
+struct HostExec {
+  std::vector<float> buf;
+  int nt;
+  HostExec(int floats, int threads) : buf((size_t)floats + 4, 0.0f), nt(threads) {
+    // poison so that reads of never-written shared memory show up as NaN in the outputs
+    for (auto& v : buf) v = __builtin_nanf("");
+  }
+  float* smem() {  // 16-byte aligned
+    uintptr_t p = reinterpret_cast<uintptr_t>(buf.data());
+    return reinterpret_cast<float*>((p + 15) & ~uintptr_t(15));
+  }
+  int nthreads() const { return nt; }
+  template <class F>
+  void phase(F f) {
+    for (int t = 0; t < nt; ++t) f(t);
+  }
+  void async16(float* dst, const float* src) { memcpy(dst, src, 16); }
+  void async_wait() {}
+};
+
+Weights one(const float* p) {
+  Weights w;
+  for (int i = 0; i < kMaxModels; ++i) w.p[i] = nullptr;
+  w.p[0] = p;
+  return w;
+}
+
+template <class Body>
+int run_block(const float* in, int B, const float* we, const float* be, const float* wd,
+              const float* bd, float* out, int splits, int threads) {
+  ExpandDwArgs a;
+  a.we = one(we); a.be = one(be); a.wd = one(wd); a.bd = one(bd);
+  a.in = in; a.out = out; a.B = B; a.splits = splits;
+  for (int cta = 0; cta < B * splits; ++cta) {
+    HostExec x(Body::kSmemFloats, threads);
+    Body::run(x, a, cta);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// cfg: 2, 3, 4 = the block of features.<cfg> (the shapes fused.cu instantiates)
+int emu_expand_dw(int cfg, const float* in, int B, const float* we, const float* be,
+                  const float* wd, const float* bd, float* out, int splits, int threads) {
+  switch (cfg) {
+    case 2: return run_block<ExpandDwBody<16, 96, 2, 50, 1, 10, 10>>(in, B, we, be, wd, bd, out, splits, threads);
+    case 3: return run_block<ExpandDwBody<24, 144, 1, 25, 2, 8, 7>>(in, B, we, be, wd, bd, out, splits, threads);
+    case 4: return run_block<ExpandDwBody<24, 144, 2, 25, 1, 8, 7>>(in, B, we, be, wd, bd, out, splits, threads);
+  }
+  return 1;
+}
+
+int emu_front(const float* vis, int B, int C, const float* ws, const float* bs, const float* wd,
+              const float* bd, const float* wp, const float* bp, float* out, int splits, int threads) {
+  FrontArgs a;
+  a.ws = one(ws); a.bs = one(bs); a.wd = one(wd); a.bd = one(bd); a.wp = one(wp); a.bp = one(bp);
+  a.vis = vis; a.out = out; a.B = B; a.C = C; a.splits = splits;
+  for (int cta = 0; cta < B * splits; ++cta) {
+    HostExec x(FrontBody::smem_floats(C), threads);
+    FrontBody::run(x, a, cta);
+  }
+  return 0;
+}
+
+}  // extern "C"

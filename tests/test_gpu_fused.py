@@ -1,0 +1,93 @@
+"""GPU parity of the fused encoder-front kernels (csrc/fused.cu): `front_kernel`
+(features.0 + features.1) and `expand_dw_kernel` (expand 1x1 + depthwise 3x3 of
+features.2-4), through the C-ABI, against the oracle's layer-by-layer MobileNetV2
+(perception.py:53-55 + torchvision, eval) and against the unfused kernels."""
+import pytest
+import torch
+
+from oracle import restatement as R
+from oatomobile_b200.synthetic import synthetic_inputs, synthetic_state_dict
+from tests.helpers import REL_TOL, assert_close
+from tests.test_fused_emu import _prefix_activations
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ensemble(sds, C, mask, pw="tcgen05"):
+  import oatomobile_b200 as ob
+  from oatomobile_b200 import _native as N
+  handles = []
+  for sd in sds:
+    m = ob.ImitativeModel(output_shape=(4, 2), in_channels=C)
+    m.load_state_dict(sd, strict=True)
+    handles.append(m.to(DEV).eval())
+  ens = N.EnsembleHandle([m.native_handle() for m in handles])
+  ens.set_pw_impl(pw)
+  ens.set_fusion(mask)
+  assert ens.fusion() == mask
+  return ens, handles
+
+
+@pytest.mark.parametrize("C,B,E", [(4, 3, 2), (2, 1, 1), (4, 5, 3)])
+@pytest.mark.parametrize("mask", [1, 2, 4, 8, 15])
+def test_prefix_activations_match_oracle(C, B, E, mask):
+  """Activation after blocks 1..4 with each fused kernel switched on alone and all together."""
+  from oatomobile_b200 import ops
+  sds = [synthetic_state_dict("dim", C, 40 + m) for m in range(E)]
+  visual = R.transform_visual(synthetic_inputs(B, C, 1, 4, seed=21)["lidar"])
+  ens, keep = _ensemble(sds, C, mask)
+  ref = [_prefix_activations(sd, visual) for sd in sds]
+  vis = visual.to(DEV)
+  for blocks in (1, 2, 3, 4):
+    got = ops.encoder_prefix(ens, vis, blocks).cpu()
+    assert not torch.isnan(got).any(), (mask, blocks)
+    for m in range(E):
+      want = ref[m]["out%d" % blocks].permute(0, 2, 3, 1)
+      assert_close(got[m], want, 2e-5, "mask %d block %d model %d" % (mask, blocks, m))
+
+
+@pytest.mark.parametrize("pw", ["tcgen05", "simt"])
+def test_fused_z_matches_unfused_and_oracle(pw):
+  from oatomobile_b200 import ops
+  C, B, E = 4, 6, 2
+  sds = [synthetic_state_dict("dim", C, 60 + m) for m in range(E)]
+  inp = synthetic_inputs(B, C, 1, 4, seed=23)
+  visual = R.transform_visual(inp["lidar"])
+  scalars = torch.cat([inp["velocity"], inp["is_at_traffic_light"], inp["traffic_light_state"]], 1)
+  zs = {}
+  for mask in (0, 15):
+    ens, keep = _ensemble(sds, C, mask, pw)
+    zs[mask] = ops.encode(ens, visual.to(DEV), scalars.to(DEV)).cpu()
+  with torch.no_grad():
+    for m in range(E):
+      want = R.imitative_params(sds[m], visual, inp["velocity"], inp["is_at_traffic_light"],
+                                inp["traffic_light_state"])
+      assert_close(zs[15][m], want, REL_TOL, "fused z[%d]" % m)
+      assert_close(zs[0][m], want, REL_TOL, "unfused z[%d]" % m)
+  assert_close(zs[15], zs[0], 5e-5, "fused vs unfused z")
+
+
+def test_fused_full_batch_determinism_and_subset():
+  """BASELINE-size batch (256 scenes would take the oracle minutes): the fused path is
+  deterministic, independent of the batch a scene sits in, and agrees with the oracle on a
+  subset of scenes."""
+  from oatomobile_b200 import ops
+  C, B, E = 4, 64, 4
+  sds = [synthetic_state_dict("dim", C, 80 + m) for m in range(E)]
+  inp = synthetic_inputs(B, C, 1, 4, seed=29)
+  visual = R.transform_visual(inp["lidar"])
+  scalars = torch.cat([inp["velocity"], inp["is_at_traffic_light"], inp["traffic_light_state"]], 1)
+  ens, keep = _ensemble(sds, C, 15)
+  v, s = visual.to(DEV), scalars.to(DEV)
+  z1 = ops.encode(ens, v, s)
+  z2 = ops.encode(ens, v, s)
+  assert torch.equal(z1, z2)
+  sub = [0, 17, 63]
+  zs = ops.encode(ens, v[sub].contiguous(), s[sub].contiguous())
+  assert torch.equal(zs, z1[:, sub])
+  with torch.no_grad():
+    for m in (0, 3):
+      want = R.imitative_params(sds[m], visual[sub], inp["velocity"][sub],
+                                inp["is_at_traffic_light"][sub], inp["traffic_light_state"][sub])
+      assert_close(z1[m, sub], want, REL_TOL, "z[%d]" % m)
