@@ -32,6 +32,184 @@ struct CudaExec {
   __device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 };
 
+// ---------------------------------------------------------------------------------------
+// Tensor-core executor: 3xTF32 tcgen05 GEMMs, accumulator in TMEM (see tc_gemm.cu for the
+// precision argument and the operand layout; K <= 72 here, so the fp32-accumulate truncation
+// of tcgen05.mma is below 1e-6 with the small correction products issued first).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int THREADS>
+struct TcExec {
+  float* sm;        // 1024-byte aligned dynamic shared memory
+  uint32_t tmem;    // TMEM base address (lane 0, first allocated column)
+  uint32_t bar;     // mbarrier the MMAs commit to
+  uint32_t parity;  // phase the next epilogue waits for
+  __device__ __forceinline__ float* smem() const { return sm; }
+  __device__ __forceinline__ int nthreads() const { return THREADS; }
+  template <class F>
+  __device__ __forceinline__ void phase(F f) {
+    f((int)threadIdx.x);
+    __syncthreads();
+  }
+  template <class F>
+  __device__ __forceinline__ void phase_nosync(F f) {
+    f((int)threadIdx.x);
+  }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+  }
+  __device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+  // v = 4 consecutive-k elements of operand row `row`; hi tile at `tile`, lo tile `rows`*128 B behind
+  __device__ __forceinline__ void op_store4(float* tile, int rows, int row, int k, fused::F4 v) {
+    const uint32_t x = __float_as_uint(v.x), y = __float_as_uint(v.y), z = __float_as_uint(v.z),
+                   w = __float_as_uint(v.w);
+    const uint32_t hx = x & 0xffffe000u, hy = y & 0xffffe000u, hz = z & 0xffffe000u, hw = w & 0xffffe000u;
+    const uint32_t lx = __float_as_uint(v.x - __uint_as_float(hx)) & 0xffffe000u;
+    const uint32_t ly = __float_as_uint(v.y - __uint_as_float(hy)) & 0xffffe000u;
+    const uint32_t lz = __float_as_uint(v.z - __uint_as_float(hz)) & 0xffffe000u;
+    const uint32_t lw = __float_as_uint(v.w - __uint_as_float(hw)) & 0xffffe000u;
+    const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)row & 7u)) << 4);
+    const uint32_t hi = smem_u32(tile) + off, lo = hi + (uint32_t)rows * 128u;
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(hi), "r"(hx), "r"(hy), "r"(hz), "r"(hw) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(lo), "r"(lx), "r"(ly), "r"(lz), "r"(lw) : "memory");
+  }
+
+  // D[acc .. acc+N) = A B^T  (A: 128 rows, B: N rows, K-major, ceil(K/32) k-blocks; K % 8 == 0)
+  __device__ __forceinline__ void mma(int acc, int N, const float* a_tile, const float* b_tile, int K) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes -> tensor core
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
+                             ((uint32_t)(fused::kTileRows >> 4) << 24);
+      const uint32_t d = tmem + (uint32_t)acc;
+      const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(b_tile);
+      const uint32_t a_kb = (uint32_t)fused::kATileFloats * 4u, b_kb = (uint32_t)fused::b_tile_floats(N) * 4u;
+      const uint32_t a_lo = (uint32_t)fused::kTileRows * 128u, b_lo = (uint32_t)N * 128u;
+      const int kbs = (K + 31) / 32;
+      uint32_t accum = 0;
+      for (int kb = 0; kb < kbs; ++kb) {  // correction products first (2^-11 of the main one)
+        const int left = K - 32 * kb, slices = left >= 32 ? 4 : left / 8;
+        const uint64_t dAh = make_desc_sw128(a0 + kb * a_kb), dAl = make_desc_sw128(a0 + kb * a_kb + a_lo);
+        const uint64_t dBh = make_desc_sw128(b0 + kb * b_kb), dBl = make_desc_sw128(b0 + kb * b_kb + b_lo);
+        for (int ks = 0; ks < slices; ++ks) {
+          const uint64_t off = (uint64_t)(2 * ks);  // 8 tf32 = 32 B = 2 x 16 B along K
+          umma_tf32(d, dAl + off, dBh + off, idesc, accum);
+          accum = 1;
+          umma_tf32(d, dAh + off, dBl + off, idesc, 1u);
+        }
+      }
+      for (int kb = 0; kb < kbs; ++kb) {
+        const int left = K - 32 * kb, slices = left >= 32 ? 4 : left / 8;
+        const uint64_t dAh = make_desc_sw128(a0 + kb * a_kb), dBh = make_desc_sw128(b0 + kb * b_kb);
+        for (int ks = 0; ks < slices; ++ks) umma_tf32(d, dAh + (uint64_t)(2 * ks), dBh + (uint64_t)(2 * ks), idesc, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+  }
+
+  // emit(row, c4, F4) for accumulator row = 32*(warp%4)+lane and every 16-column chunk of the
+  // warp's column group (warp/4); the caller adds a barrier before the accumulator is reused
+  template <class Emit>
+  __device__ __forceinline__ void epilogue(int acc, int N, Emit emit) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+    parity ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    const int quad = warp & 3, grp = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc;
+    for (int c = grp; c < N / 16; c += THREADS / 128) {
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+            "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+            "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr + (uint32_t)(16 * c)));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        emit(row, 4 * c + j,
+             fused::F4{__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])});
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+};
+
+constexpr int kTcThreads = 512;
+
+template <class Body>
+__global__ void __launch_bounds__(kTcThreads, 1) expand_dw_tc_kernel(const __grid_constant__ fused::ExpandDwArgs a) {
+  extern __shared__ __align__(16) uint8_t tc_smem_raw[];
+  __shared__ uint64_t mma_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = (int)threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mma_bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {  // TMEM allocation is a warp-wide operation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(Body::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uintptr_t base = (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023);
+  TcExec<kTcThreads> x{reinterpret_cast<float*>(base), tmem_slot, smem_u32(&mma_bar), 0u};
+  Body::run(x, a, (int)blockIdx.x);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(x.tmem), "r"(Body::kTmemCols) : "memory");
+  }
+}
+
 template <class Body>
 __global__ void __launch_bounds__(kFusedThreads, 2) expand_dw_kernel(const __grid_constant__ fused::ExpandDwArgs a) {
   extern __shared__ __align__(16) float fused_smem[];
@@ -77,6 +255,21 @@ fused::Weights table(const PtrTable& t) {
 }
 
 template <class Body>
+int launch_tc_body(const FusedBlockLaunch& l, cudaStream_t stream) {
+  fused::ExpandDwArgs a;
+  a.we = table(l.we); a.be = table(l.be); a.wd = table(l.wd); a.bd = table(l.bd);
+  a.in = l.in; a.out = l.out; a.B = l.B;
+  a.splits = splits_for(Body::GROUPS);
+  const int smem = Body::kSmemFloats * (int)sizeof(float) + 1024;  // + alignment slack
+  static int configured[64] = {0};
+  if (int rc = allow_smem(expand_dw_tc_kernel<Body>, smem, configured)) return rc;
+  const int64_t ctas = (int64_t)l.E * l.B * a.splits;
+  expand_dw_tc_kernel<Body><<<(unsigned)ctas, kTcThreads, smem, stream>>>(a);
+  OAT_LAUNCH_CHECK();
+  return 0;
+}
+
+template <class Body>
 int launch_body(const FusedBlockLaunch& l, cudaStream_t stream) {
   fused::ExpandDwArgs a;
   a.we = table(l.we); a.be = table(l.be); a.wd = table(l.wd); a.bd = table(l.bd);
@@ -101,6 +294,16 @@ bool fused_block_supported(int cin, int hid, int stride, int hin) {
 
 int launch_fused_expand_dw(const FusedBlockLaunch& l, cudaStream_t stream) {
   if (l.E <= 0 || l.B <= 0) return 0;
+  if (l.tensor_cores) {
+    //                                        CIN  HID  S  HIN OR ORD NSEG
+    if (l.cin == 16 && l.hid == 96 && l.stride == 2 && l.hin == 50)
+      return launch_tc_body<fused::ExpandDwTcBody<16, 96, 2, 50, 1, 1, 21>>(l, stream);
+    if (l.cin == 24 && l.hid == 144 && l.stride == 1 && l.hin == 25)
+      return launch_tc_body<fused::ExpandDwTcBody<24, 144, 1, 25, 4, 2, 7>>(l, stream);
+    if (l.cin == 24 && l.hid == 144 && l.stride == 2 && l.hin == 25)
+      return launch_tc_body<fused::ExpandDwTcBody<24, 144, 2, 25, 2, 1, 7>>(l, stream);
+    return fail("launch_fused_expand_dw: unsupported block shape");
+  }
   //                                    CIN  HID  S  HIN OR  TP NSEG
   if (l.cin == 16 && l.hid == 96 && l.stride == 2 && l.hin == 50)
     return launch_body<fused::ExpandDwBody<16, 96, 2, 50, 1, 10, 10>>(l, stream);

@@ -120,45 +120,46 @@ OAT_FHD void gemm_rows(const float* A, int lda, const float* W, int ldw, const f
 }
 
 // ---------------------------------------------------------------------------------------
-// Depthwise 3x3 (pad 1, stride S) + bias + ReLU6 over a ring of NR = S*(OR-1)+3 image rows
-// in shared memory, producing OR output rows.  ring: [NR slots][win][ld] floats, the input
-// row `ir` sits in slot (ir mod NR); rows outside the image hold zeros (the caller fills
-// them), columns outside the image read as zeros here.  Work item = (column segment, c4),
-// c4 fastest; the 3-column window slides along the segment in registers.
-// wd: [9][hid] (tap-major), bd: [hid], both in shared memory.
-// emit(o, oc, c4, v): output row orow0 + o (o < OR), column oc.
+// Depthwise 3x3 (pad 1, stride S) + bias + ReLU6 over a ring of RING image rows in shared
+// memory.  One call produces nsub * ORD output rows: sub-pass `sub` reads the NW = S*(ORD-1)+3
+// input rows starting at ir0 + sub*S*ORD and emits output rows sub*ORD .. sub*ORD+ORD-1.
+// ring: [RING slots][win][ld] floats, the input row `ir` sits in slot (ir mod RING); rows
+// outside the image hold zeros (the caller fills them), columns outside the image read as
+// zeros here.  Work item = (sub-pass, column segment, c4), c4 fastest; the 3-column window
+// slides along the segment in registers.  wd: [9][hid] (tap-major), bd: [hid], shared memory.
+// emit(o, oc, c4, v): o-th output row of the call, column oc.
 // ---------------------------------------------------------------------------------------
-template <int S, int OR, class Emit>
+template <int S, int ORD, int RING, class Emit>
 OAT_FHD void dw_rows(const float* ring, int ld, int win, int wout, const float* wd, const float* bd,
-                     int hid, int ir0, int nseg, int tid, int nthreads, Emit emit) {
-  constexpr int NR = S * (OR - 1) + 3;
+                     int hid, int ir0, int nsub, int nseg, int tid, int nthreads, Emit emit) {
+  constexpr int NW = S * (ORD - 1) + 3;
   const int N4 = hid >> 2;
-  for (int item = tid; item < nseg * N4; item += nthreads) {
-    const int seg = item / N4, c4 = item - seg * N4;
+  for (int item = tid; item < nsub * nseg * N4; item += nthreads) {
+    const int c4 = item % N4, seg = (item / N4) % nseg, sub = item / (N4 * nseg);
     const int c_lo = (seg * wout) / nseg, c_hi = ((seg + 1) * wout) / nseg;
     if (c_lo >= c_hi) continue;
     F4 k[9];
     OAT_FUNROLL
     for (int t = 0; t < 9; ++t) k[t] = ld4(wd + t * hid + 4 * c4);
     const F4 bv = ld4(bd + 4 * c4);
-    const float* rowp[NR];
+    const float* rowp[NW];
     OAT_FUNROLL
-    for (int r = 0; r < NR; ++r) {
-      const int slot = ((ir0 + r) % NR + NR) % NR;
+    for (int r = 0; r < NW; ++r) {
+      const int slot = ((ir0 + sub * S * ORD + r) % RING + RING) % RING;
       rowp[r] = ring + (slot * win) * ld + 4 * c4;
     }
-    F4 c0[NR], c1[NR], c2[NR];
-    auto ldcol = [&](int ic, F4(&col)[NR]) {
+    F4 c0[NW], c1[NW], c2[NW];
+    auto ldcol = [&](int ic, F4(&col)[NW]) {
       const bool ok = ic >= 0 && ic < win;
       OAT_FUNROLL
-      for (int r = 0; r < NR; ++r) col[r] = ok ? ld4(rowp[r] + ic * ld) : zero4();
+      for (int r = 0; r < NW; ++r) col[r] = ok ? ld4(rowp[r] + ic * ld) : zero4();
     };
     ldcol(S * c_lo - 1, c0);
     ldcol(S * c_lo, c1);
     for (int oc = c_lo; oc < c_hi; ++oc) {
       ldcol(S * oc + 1, c2);
       OAT_FUNROLL
-      for (int o = 0; o < OR; ++o) {
+      for (int o = 0; o < ORD; ++o) {
         F4 acc = bv;
         OAT_FUNROLL
         for (int kh = 0; kh < 3; ++kh) {
@@ -166,14 +167,14 @@ OAT_FHD void dw_rows(const float* ring, int ld, int win, int wout, const float* 
           acc = fma4(c1[S * o + kh], k[3 * kh + 1], acc);
           acc = fma4(c2[S * o + kh], k[3 * kh + 2], acc);
         }
-        emit(o, oc, c4, relu6_4(acc));
+        emit(sub * ORD + o, oc, c4, relu6_4(acc));
       }
       if (S == 1) {
         OAT_FUNROLL
-        for (int r = 0; r < NR; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
+        for (int r = 0; r < NW; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
       } else {
         OAT_FUNROLL
-        for (int r = 0; r < NR; ++r) c0[r] = c2[r];
+        for (int r = 0; r < NW; ++r) c0[r] = c2[r];
         if (oc + 1 < c_hi) ldcol(S * (oc + 1), c1);
       }
     }
@@ -286,7 +287,7 @@ struct ExpandDwBody {
         expand(tid, buf, ir0 + PRIME, NEW);
       });
       x.phase([&](int tid) {
-        dw_rows<S, OR>(ring, LDE, HIN, HOUT, Wd, Bd, HID, ir0, NSEG, tid, nt,
+        dw_rows<S, OR, NR>(ring, LDE, HIN, HOUT, Wd, Bd, HID, ir0, 1, NSEG, tid, nt,
                        [&](int o, int oc, int c4, F4 v) {
                          const int orow = g * OR + o;
                          if (orow < HOUT) gstore4(out + ((int64_t)orow * HOUT + oc) * HID + 4 * c4, v);
@@ -420,7 +421,7 @@ struct FrontBody {
       });
       x.phase([&](int tid) { stem(tid, sr); });
       x.phase([&](int tid) {
-        dw_rows<1, 2>(ring, LDS_, HS, HS, Wd, Bd, 32, 2 * p - 1, 16, tid, nt,
+        dw_rows<1, 2, NR>(ring, LDS_, HS, HS, Wd, Bd, 32, 2 * p - 1, 1, 16, tid, nt,
                       [&](int o, int oc, int c4, F4 v) { st4(D + (o * HS + oc) * LDS_ + 4 * c4, v); });
       });
       x.phase([&](int tid) {
@@ -430,6 +431,166 @@ struct FrontBody {
         x.async_wait();
       });
     }
+  }
+};
+
+
+// =======================================================================================
+// Tensor-core variants.  Same walk over the image, but the pointwise convolution of the new
+// rows is ONE M=128 tcgen05 GEMM per iteration (3xTF32, accumulator in TMEM) instead of FP32
+// FMAs, issued asynchronously so that it overlaps the depthwise pass of the previous group.
+// The executor additionally provides
+//   op_store4(tile, rows, row, k, v)   4 consecutive-k elements of an operand row: A tiles
+//                                      [128 rows][32 k] and weight tiles [N rows][32 k] per
+//                                      k-block (device: TF32 hi/lo split, K-major 128B-swizzled
+//                                      UMMA layout, lo tile right behind the hi tile);
+//   mma(acc, N, a, b, K)               D[acc .. acc+N) (128 x N) = A B^T over ceil(K/32) k-blocks
+//                                      (device: proxy fence + barrier, one thread issues);
+//   epilogue(acc, N, emit)             emit(row, c4, F4) for every accumulator row / 4 columns
+//                                      (device: waits for the MMAs, tcgen05.ld, one row per lane).
+// The host executor implements the three with plain loops (tests/emu).
+// =======================================================================================
+constexpr int kTileRows = 128;                      // UMMA M
+constexpr int kATileFloats = 2 * kTileRows * 32;    // hi + lo halves of one A k-block
+OAT_FHD constexpr int b_tile_floats(int n) { return 2 * n * 32; }
+
+template <int CIN_, int HID_, int S_, int HIN_, int OR_, int ORD_, int NSEG_>
+struct ExpandDwTcBody {
+  static constexpr int CIN = CIN_, HID = HID_, S = S_, HIN = HIN_, OR = OR_, ORD = ORD_, NSEG = NSEG_;
+  static constexpr int HOUT = (HIN - 1) / S + 1;
+  static constexpr int NR = S * (OR - 1) + 3;   // ring rows
+  static constexpr int NEW = S * OR;            // new input rows per iteration
+  static constexpr int PRIME = NR - NEW;        // rows of the priming pass (3 - S)
+  static constexpr int LDX = CIN + 4;
+  static constexpr int LDE = HID + 4;
+  static constexpr int GROUPS = (HOUT + OR - 1) / OR;
+  static constexpr int NSUB = OR / ORD;
+  static_assert(PRIME >= 1 && PRIME <= NEW, "stride 1 needs OR >= 2");
+  static_assert(NEW * HIN <= kTileRows, "one iteration must fit one M=128 tile");
+  static_assert(OR % ORD == 0, "depthwise sub-passes must tile the group");
+  static_assert(CIN % 8 == 0 && CIN <= 32, "one k-block of TF32 k-slices");
+  static_assert(HID % 16 == 0 && HID <= 256, "UMMA N");
+  // shared-memory map (floats); operand tiles are 1024-byte aligned
+  static constexpr int kA = 0;
+  static constexpr int kB = kA + kATileFloats;
+  static constexpr int kBe = kB + b_tile_floats(HID);
+  static constexpr int kWd = kBe + HID;
+  static constexpr int kBd = kWd + 9 * HID;
+  static constexpr int kX = kBd + HID;
+  static constexpr int kXFloats = NEW * HIN * LDX;
+  static constexpr int kRing = kX + 2 * kXFloats;
+  static constexpr int kSmemFloats = kRing + NR * HIN * LDE;
+  static constexpr int kTmemCols = HID <= 128 ? 128 : 256;
+
+  template <class X>
+  OAT_FHD static void run(X& x, const ExpandDwArgs& a, int cta) {
+    float* sm = x.smem();
+    const int nt = x.nthreads();
+    const int split = cta % a.splits;
+    const int img = cta / a.splits;  // model * B + b
+    const int model = img / a.B;
+    const float* in = a.in + (int64_t)img * HIN * HIN * CIN;
+    float* out = a.out + (int64_t)img * HOUT * HOUT * HID;
+    const int g0 = (split * GROUPS) / a.splits, g1 = ((split + 1) * GROUPS) / a.splits;
+    if (g0 >= g1) return;
+    float* At = sm + kA;
+    float* Bt = sm + kB;
+    float* Be = sm + kBe;
+    float* Wd = sm + kWd;
+    float* Bd = sm + kBd;
+    float* ring = sm + kRing;
+
+    auto stage = [&](int tid, int buf, int lo, int n) {
+      const int vlo = lo < 0 ? 0 : lo;
+      const int vhi = lo + n > HIN ? HIN : lo + n;
+      if (vhi <= vlo) return;
+      float* dst = sm + kX + buf * kXFloats;
+      const float* src = in + (int64_t)vlo * HIN * CIN;
+      const int chunks = (vhi - vlo) * HIN * (CIN / 4);
+      for (int i = tid; i < chunks; i += nt) {
+        const int px = i / (CIN / 4), q = i - px * (CIN / 4);
+        x.async16(dst + px * LDX + 4 * q, src + px * CIN + 4 * q);
+      }
+    };
+    auto valid_pixels = [&](int lo, int n, int* vlo_out) {
+      const int vlo = lo < 0 ? 0 : lo;
+      const int vhi = lo + n > HIN ? HIN : lo + n;
+      *vlo_out = vlo;
+      return vhi > vlo ? (vhi - vlo) * HIN : 0;
+    };
+    // rows [lo, lo+n): staged pixels -> A tile, then the expand GEMM is issued
+    auto issue = [&](int buf, int lo, int n) {
+      int vlo;
+      const int np = valid_pixels(lo, n, &vlo);
+      if (np == 0) return;
+      const float* Xs = sm + kX + buf * kXFloats;
+      x.phase_nosync([&](int tid) {
+        for (int i = tid; i < np * (CIN / 4); i += nt) {
+          const int px = i / (CIN / 4), q = i - px * (CIN / 4);
+          x.op_store4(At, kTileRows, px, 4 * q, ld4(Xs + px * LDX + 4 * q));
+        }
+      });
+      x.mma(0, HID, At, Bt, CIN);
+    };
+    // accumulator -> ring rows (bias + ReLU6); rows outside the image become zeros
+    auto collect = [&](int lo, int n) {
+      int vlo;
+      const int np = valid_pixels(lo, n, &vlo);
+      if (np > 0)
+        x.epilogue(0, HID, [&](int p, int c4, F4 v) {
+          if (p >= np) return;
+          const int r = p / HIN, col = p - r * HIN;
+          const int slot = (vlo + r) % NR;
+          const F4 b = ld4(Be + 4 * c4);
+          st4(ring + (slot * HIN + col) * LDE + 4 * c4,
+              relu6_4(F4{v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w}));
+        });
+      x.phase([&](int tid) {
+        for (int ir = lo; ir < lo + n; ++ir) {
+          if (ir >= 0 && ir < HIN) continue;
+          float* row = ring + (((ir % NR) + NR) % NR) * HIN * LDE;
+          for (int i = tid; i < HIN * LDE / 4; i += nt) st4(row + 4 * i, zero4());
+        }
+      });
+    };
+    auto depthwise = [&](int tid, int g) {
+      dw_rows<S, ORD, NR>(ring, LDE, HIN, HOUT, Wd, Bd, HID, S * g * OR - 1, NSUB, NSEG, tid, nt,
+                          [&](int o, int oc, int c4, F4 v) {
+                            const int orow = g * OR + o;
+                            if (orow < HOUT) gstore4(out + ((int64_t)orow * HOUT + oc) * HID + 4 * c4, v);
+                          });
+    };
+
+    const int ir_first = S * g0 * OR - 1;
+    x.phase([&](int tid) {
+      const float *we = a.we.p[model], *be = a.be.p[model], *wd = a.wd.p[model], *bd = a.bd.p[model];
+      for (int i = tid; i < (CIN / 4) * HID; i += nt) {  // W_e [CIN][HID] -> weight tile rows n
+        const int n = i % HID, k4 = i / HID;
+        const F4 v{gload(we + (4 * k4 + 0) * HID + n), gload(we + (4 * k4 + 1) * HID + n),
+                   gload(we + (4 * k4 + 2) * HID + n), gload(we + (4 * k4 + 3) * HID + n)};
+        x.op_store4(Bt, HID, n, 4 * k4, v);
+      }
+      for (int i = tid; i < HID / 4; i += nt) st4(Be + 4 * i, gload4(be + 4 * i));
+      for (int i = tid; i < 9 * HID / 4; i += nt) st4(Wd + 4 * i, gload4(wd + 4 * i));
+      for (int i = tid; i < HID / 4; i += nt) st4(Bd + 4 * i, gload4(bd + 4 * i));
+      stage(tid, 0, ir_first, PRIME);
+      stage(tid, 1, ir_first + PRIME, NEW);
+      x.async_wait();
+    });
+    issue(0, ir_first, PRIME);
+    collect(ir_first, PRIME);
+    for (int g = g0; g < g1; ++g) {
+      const int buf = (g - g0 + 1) & 1;
+      const int ir0 = S * g * OR - 1;
+      issue(buf, ir0 + PRIME, NEW);  // asynchronous: overlaps the depthwise pass below
+      x.phase([&](int tid) {
+        if (g + 1 < g1) stage(tid, buf ^ 1, ir0 + NEW + PRIME, NEW);
+        if (g > g0) depthwise(tid, g - 1);
+        x.async_wait();
+      });
+      collect(ir0 + PRIME, NEW);
+    }
+    x.phase([&](int tid) { depthwise(tid, g1 - 1); });
   }
 };
 

@@ -33,6 +33,34 @@ struct HostExec {
   }
   void async16(float* dst, const float* src) { memcpy(dst, src, 16); }
   void async_wait() {}
+
+  // ---- tensor-core interface, plain loops: operand tiles are [rows][32] per k-block (the lo
+  // halves stay unused), the GEMM runs when the accumulator is collected.
+  template <class F>
+  void phase_nosync(F f) { phase(f); }
+  void sync() {}
+  void op_store4(float* tile, int /*rows*/, int row, int k, F4 v) { st4(tile + row * 32 + k, v); }
+  const float *mma_a = nullptr, *mma_b = nullptr;
+  int mma_k = 0, mma_n = 0, mma_acc = -1;
+  void mma(int acc, int N, const float* a, const float* b, int K) {
+    mma_a = a; mma_b = b; mma_k = K; mma_n = N; mma_acc = acc;
+  }
+  template <class Emit>
+  void epilogue(int acc, int N, Emit emit) {
+    if (acc != mma_acc || N != mma_n) abort();  // collected something that was not issued
+    for (int row = 0; row < kTileRows; ++row)
+      for (int c4 = 0; c4 < N / 4; ++c4) {
+        float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int k = 0; k < mma_k; ++k) {
+          const int kb = k / 32, kk = k % 32;
+          const float av = mma_a[kb * kATileFloats + row * 32 + kk];
+          for (int j = 0; j < 4; ++j)
+            o[j] = fmaf(av, mma_b[kb * b_tile_floats(N) + (4 * c4 + j) * 32 + kk], o[j]);
+        }
+        emit(row, c4, F4{o[0], o[1], o[2], o[3]});
+      }
+    mma_acc = -1;
+  }
 };
 
 Weights one(const float* p) {
@@ -58,6 +86,17 @@ int run_block(const float* in, int B, const float* we, const float* be, const fl
 }  // namespace
 
 extern "C" {
+
+// tensor-core bodies (host GEMM); cfg as below
+int emu_expand_dw_tc(int cfg, const float* in, int B, const float* we, const float* be,
+                     const float* wd, const float* bd, float* out, int splits, int threads) {
+  switch (cfg) {
+    case 2: return run_block<ExpandDwTcBody<16, 96, 2, 50, 1, 1, 21>>(in, B, we, be, wd, bd, out, splits, threads);
+    case 3: return run_block<ExpandDwTcBody<24, 144, 1, 25, 4, 2, 7>>(in, B, we, be, wd, bd, out, splits, threads);
+    case 4: return run_block<ExpandDwTcBody<24, 144, 2, 25, 2, 1, 7>>(in, B, we, be, wd, bd, out, splits, threads);
+  }
+  return 1;
+}
 
 // cfg: 2, 3, 4 = the block of features.<cfg> (the shapes fused.cu instantiates)
 int emu_expand_dw(int cfg, const float* in, int B, const float* we, const float* be,

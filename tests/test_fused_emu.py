@@ -67,12 +67,13 @@ def test_front_other_channel_counts(C):
   assert _err(got, want) < 2e-5
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("idx", [2, 3, 4])
-@pytest.mark.parametrize("splits,threads", [(1, 256), (2, 256), (4, 64), (3, 37)])
-def test_expand_dw_matches_oracle(case, idx, splits, threads):
+@pytest.mark.parametrize("splits,threads", [(1, 256), (2, 512), (4, 64), (3, 37)])
+def test_expand_dw_matches_oracle(case, idx, splits, threads, tc):
   sd, _, acts = case
   x = acts["out%d" % (idx - 1)].permute(0, 2, 3, 1).contiguous()
-  got = FD.expand_dw(idx, sd, x, splits=splits, threads=threads)
+  got = FD.expand_dw(idx, sd, x, splits=splits, threads=threads, tc=tc)
   assert not torch.isnan(got).any()
   want = acts["dw%d" % idx].permute(0, 2, 3, 1)
   assert got.shape == want.shape

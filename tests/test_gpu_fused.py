@@ -29,14 +29,16 @@ def _ensemble(sds, C, mask, pw="tcgen05"):
   return ens, handles
 
 
+@pytest.mark.parametrize("pw", ["tcgen05", "simt"])
 @pytest.mark.parametrize("C,B,E", [(4, 3, 2), (2, 1, 1), (4, 5, 3)])
 @pytest.mark.parametrize("mask", [1, 2, 4, 8, 15])
-def test_prefix_activations_match_oracle(C, B, E, mask):
-  """Activation after blocks 1..4 with each fused kernel switched on alone and all together."""
+def test_prefix_activations_match_oracle(C, B, E, mask, pw):
+  """Activation after blocks 1..4 with each fused kernel switched on alone and all together,
+  with the fused pointwise GEMMs on the tensor cores (3xTF32) and as FP32 FMAs."""
   from oatomobile_b200 import ops
   sds = [synthetic_state_dict("dim", C, 40 + m) for m in range(E)]
   visual = R.transform_visual(synthetic_inputs(B, C, 1, 4, seed=21)["lidar"])
-  ens, keep = _ensemble(sds, C, mask)
+  ens, keep = _ensemble(sds, C, mask, pw)
   ref = [_prefix_activations(sd, visual) for sd in sds]
   vis = visual.to(DEV)
   for blocks in (1, 2, 3, 4):
