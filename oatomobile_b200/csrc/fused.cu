@@ -74,24 +74,55 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-template <int THREADS>
-struct TcExec {
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+constexpr int kPipeThreads = 512;   // warps 0-7: producer half, warps 8-15: consumer half
+constexpr int kHalf = kPipeThreads / 2;
+
+// Executor of the pipelined tensor-core bodies (fused_body.h, "Executor interface").
+struct PipeExec {
+  static constexpr bool kConcurrent = true;
   float* sm;        // 1024-byte aligned dynamic shared memory
   uint32_t tmem;    // TMEM base address (lane 0, first allocated column)
-  uint32_t bar;     // mbarrier the MMAs commit to
-  uint32_t parity;  // phase the next epilogue waits for
+  uint32_t bars;    // shared address of: [0] GEMM complete, [1,2] ready, [3,4] done (8 B each)
+  uint32_t parity;  // phase of the GEMM barrier the next epilogue waits for (producer only)
   __device__ __forceinline__ float* smem() const { return sm; }
-  __device__ __forceinline__ int nthreads() const { return THREADS; }
+  __device__ __forceinline__ bool is_producer() const { return threadIdx.x < kHalf; }
+  __device__ __forceinline__ int p_threads() const { return kHalf; }
+  __device__ __forceinline__ int c_threads() const { return kHalf; }
+  __device__ __forceinline__ void p_barrier() const { asm volatile("bar.sync 1, %0;" ::"n"(kHalf) : "memory"); }
   template <class F>
-  __device__ __forceinline__ void phase(F f) {
-    f((int)threadIdx.x);
+  __device__ __forceinline__ void all_phase(F f) {
+    __syncthreads();
+    f((int)threadIdx.x, kPipeThreads);
     __syncthreads();
   }
   template <class F>
-  __device__ __forceinline__ void phase_nosync(F f) {
+  __device__ __forceinline__ void p_phase(F f) {
+    f((int)threadIdx.x);
+    p_barrier();
+  }
+  template <class F>
+  __device__ __forceinline__ void p_phase_nosync(F f) {
     f((int)threadIdx.x);
   }
-  __device__ __forceinline__ void sync() { __syncthreads(); }
+  template <class F>
+  __device__ __forceinline__ void c_run(F f) {
+    f((int)threadIdx.x - kHalf);
+  }
+  __device__ __forceinline__ void signal_ready(uint32_t i) { mbar_arrive(bars + 8u * (1u + (i & 1u))); }
+  __device__ __forceinline__ void wait_ready(uint32_t i) { mbar_wait(bars + 8u * (1u + (i & 1u)), (i >> 1) & 1u); }
+  __device__ __forceinline__ void signal_done(uint32_t i) { mbar_arrive(bars + 8u * (3u + (i & 1u))); }
+  __device__ __forceinline__ void wait_done(uint32_t i) { mbar_wait(bars + 8u * (3u + (i & 1u)), (i >> 1) & 1u); }
   __device__ __forceinline__ void async16(float* dst, const float* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
   }
@@ -112,10 +143,11 @@ struct TcExec {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(lo), "r"(lx), "r"(ly), "r"(lz), "r"(lw) : "memory");
   }
 
-  // D[acc .. acc+N) = A B^T  (A: 128 rows, B: N rows, K-major, ceil(K/32) k-blocks; K % 8 == 0)
+  // producer half: D[acc .. acc+N) = A B^T  (A: 128 rows, B: N rows, K-major, ceil(K/32)
+  // k-blocks; K % 8 == 0).  Asynchronous: completion is observed by epilogue().
   __device__ __forceinline__ void mma(int acc, int N, const float* a_tile, const float* b_tile, int K) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes -> tensor core
-    __syncthreads();
+    p_barrier();
     if (threadIdx.x == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
@@ -142,23 +174,23 @@ struct TcExec {
         const uint64_t dAh = make_desc_sw128(a0 + kb * a_kb), dBh = make_desc_sw128(b0 + kb * b_kb);
         for (int ks = 0; ks < slices; ++ks) umma_tf32(d, dAh + (uint64_t)(2 * ks), dBh + (uint64_t)(2 * ks), idesc, 1u);
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bars) : "memory");
     }
   }
 
-  // emit(row, c4, F4) for accumulator row = 32*(warp%4)+lane and every 16-column chunk of the
-  // warp's column group (warp/4); the caller adds a barrier before the accumulator is reused
+  // producer half: emit(row, c4, F4) for accumulator row = 32*(warp%4)+lane and every other
+  // 16-column chunk (warp/4 picks the parity); a producer barrier must follow before the
+  // accumulator or the operand tiles are reused (the bodies' collect() ends with one)
   template <class Emit>
   __device__ __forceinline__ void epilogue(int acc, int N, Emit emit) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
+    mbar_wait(bars, parity);
     parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
     const int quad = warp & 3, grp = warp >> 2;
     const int row = quad * 32 + lane;
     const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc;
-    for (int c = grp; c < N / 16; c += THREADS / 128) {
+    for (int c = grp; c < N / 16; c += kHalf / 128) {
       uint32_t r[16];
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -178,16 +210,15 @@ struct TcExec {
   }
 };
 
-constexpr int kTcThreads = 512;
-
 template <class Body>
-__global__ void __launch_bounds__(kTcThreads, 1) expand_dw_tc_kernel(const __grid_constant__ fused::ExpandDwArgs a) {
+__global__ void __launch_bounds__(kPipeThreads, 1) expand_dw_tc_kernel(const __grid_constant__ fused::ExpandDwArgs a) {
   extern __shared__ __align__(16) uint8_t tc_smem_raw[];
-  __shared__ uint64_t mma_bar;
+  __shared__ uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
   const int warp = (int)threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mma_bar)), "r"(1));
+    mbar_init(smem_u32(&bars[0]), 1);
+    for (int i = 1; i < 5; ++i) mbar_init(smem_u32(&bars[i]), kHalf);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {  // TMEM allocation is a warp-wide operation
@@ -200,8 +231,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) expand_dw_tc_kernel(const __gri
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uintptr_t base = (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023);
-  TcExec<kTcThreads> x{reinterpret_cast<float*>(base), tmem_slot, smem_u32(&mma_bar), 0u};
-  Body::run(x, a, (int)blockIdx.x);
+  PipeExec x{reinterpret_cast<float*>(base), tmem_slot, smem_u32(&bars[0]), 0u};
+  Body::run(x, a, (int)blockIdx.x, (int)gridDim.x);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -260,11 +291,21 @@ int launch_tc_body(const FusedBlockLaunch& l, cudaStream_t stream) {
   a.we = table(l.we); a.be = table(l.be); a.wd = table(l.wd); a.bd = table(l.bd);
   a.in = l.in; a.out = l.out; a.B = l.B;
   a.splits = splits_for(Body::GROUPS);
+  const int64_t units = (int64_t)l.E * l.B * a.splits;
+  if (units > 0x7fffffff) return fail("fused encoder kernel: batch too large");
+  a.units = (int)units;
   const int smem = Body::kSmemFloats * (int)sizeof(float) + 1024;  // + alignment slack
   static int configured[64] = {0};
   if (int rc = allow_smem(expand_dw_tc_kernel<Body>, smem, configured)) return rc;
-  const int64_t ctas = (int64_t)l.E * l.B * a.splits;
-  expand_dw_tc_kernel<Body><<<(unsigned)ctas, kTcThreads, smem, stream>>>(a);
+  static int num_sms[64] = {0};
+  int dev = 0;
+  OAT_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && num_sms[dev] == 0)
+    OAT_CUDA(cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int sms = (dev >= 0 && dev < 64) ? num_sms[dev] : 148;
+  // persistent: one CTA per SM walks the units with a stride (weights reloaded per model only)
+  const int grid = a.units < sms ? a.units : sms;
+  expand_dw_tc_kernel<Body><<<grid, kPipeThreads, smem, stream>>>(a);
   OAT_LAUNCH_CHECK();
   return 0;
 }
@@ -275,6 +316,7 @@ int launch_body(const FusedBlockLaunch& l, cudaStream_t stream) {
   a.we = table(l.we); a.be = table(l.be); a.wd = table(l.wd); a.bd = table(l.bd);
   a.in = l.in; a.out = l.out; a.B = l.B;
   a.splits = splits_for(Body::GROUPS);
+  a.units = l.E * l.B * a.splits;
   const int smem = Body::kSmemFloats * (int)sizeof(float);
   static int configured[64] = {0};
   if (int rc = allow_smem(expand_dw_kernel<Body>, smem, configured)) return rc;
@@ -295,13 +337,13 @@ bool fused_block_supported(int cin, int hid, int stride, int hin) {
 int launch_fused_expand_dw(const FusedBlockLaunch& l, cudaStream_t stream) {
   if (l.E <= 0 || l.B <= 0) return 0;
   if (l.tensor_cores) {
-    //                                        CIN  HID  S  HIN OR ORD NSEG
+    //                                          CIN  HID  S  HIN OR NSEG
     if (l.cin == 16 && l.hid == 96 && l.stride == 2 && l.hin == 50)
-      return launch_tc_body<fused::ExpandDwTcBody<16, 96, 2, 50, 1, 1, 21>>(l, stream);
+      return launch_tc_body<fused::ExpandDwPipeBody<16, 96, 2, 50, 1, 10>>(l, stream);
     if (l.cin == 24 && l.hid == 144 && l.stride == 1 && l.hin == 25)
-      return launch_tc_body<fused::ExpandDwTcBody<24, 144, 1, 25, 4, 2, 7>>(l, stream);
+      return launch_tc_body<fused::ExpandDwPipeBody<24, 144, 1, 25, 2, 7>>(l, stream);
     if (l.cin == 24 && l.hid == 144 && l.stride == 2 && l.hin == 25)
-      return launch_tc_body<fused::ExpandDwTcBody<24, 144, 2, 25, 2, 1, 7>>(l, stream);
+      return launch_tc_body<fused::ExpandDwPipeBody<24, 144, 2, 25, 1, 7>>(l, stream);
     return fail("launch_fused_expand_dw: unsupported block shape");
   }
   //                                    CIN  HID  S  HIN OR  TP NSEG

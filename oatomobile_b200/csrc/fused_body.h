@@ -193,7 +193,8 @@ struct ExpandDwArgs {
   const float* in;
   float* out;
   int B;       // images per model
-  int splits;  // CTAs per image
+  int splits;  // work units per image (contiguous ranges of output-row groups)
+  int units;   // E * B * splits (persistent kernels walk them with a stride)
 };
 
 template <int CIN_, int HID_, int S_, int HIN_, int OR_, int TP_, int NSEG_>
@@ -436,38 +437,51 @@ struct FrontBody {
 
 
 // =======================================================================================
-// Tensor-core variants.  Same walk over the image, but the pointwise convolution of the new
-// rows is ONE M=128 tcgen05 GEMM per iteration (3xTF32, accumulator in TMEM) instead of FP32
-// FMAs, issued asynchronously so that it overlaps the depthwise pass of the previous group.
-// The executor additionally provides
+// Tensor-core, pipelined variant (the default on the GPU).
+//
+// Same walk over the image, but (1) the pointwise convolution of the new rows is ONE M=128
+// tcgen05 GEMM per row group (3xTF32, accumulator in TMEM) and (2) the CTA is split into a
+// PRODUCER half (stages input rows, writes the UMMA operand, issues the GEMM, moves the
+// accumulator through bias + ReLU6 into the row ring) and a CONSUMER half (slides the 3x3
+// depthwise window over the ring and stores the block's depthwise output), coupled by
+// ready/done barriers per row group, so the latency-bound producer chain of group g+1 hides
+// behind the FMA-bound depthwise pass of group g.  The ring holds NR + NEW rows: the window
+// of the group being consumed plus the new rows of the next one.  CTAs are persistent: each
+// walks work units (model, image, row split) with a stride and reloads weights only when
+// the model changes.
+//
+// Executor interface beyond smem()/async16()/async_wait():
+//   kConcurrent                 true: the two halves run concurrently (CUDA); false: one
+//                               sequential thread of control (host), producer one group ahead
+//   all_phase(f)                barrier; f(tid, nthreads) on every thread of the CTA; barrier
+//   is_producer(), p_threads(), p_phase(f), p_phase_nosync(f)   producer half (own barrier)
+//   c_threads(), c_run(f)       consumer half
 //   op_store4(tile, rows, row, k, v)   4 consecutive-k elements of an operand row: A tiles
-//                                      [128 rows][32 k] and weight tiles [N rows][32 k] per
-//                                      k-block (device: TF32 hi/lo split, K-major 128B-swizzled
-//                                      UMMA layout, lo tile right behind the hi tile);
-//   mma(acc, N, a, b, K)               D[acc .. acc+N) (128 x N) = A B^T over ceil(K/32) k-blocks
-//                                      (device: proxy fence + barrier, one thread issues);
-//   epilogue(acc, N, emit)             emit(row, c4, F4) for every accumulator row / 4 columns
-//                                      (device: waits for the MMAs, tcgen05.ld, one row per lane).
-// The host executor implements the three with plain loops (tests/emu).
+//                               [128 rows][32 k], weight tiles [N rows][32 k] per k-block (device:
+//                               TF32 hi/lo split, K-major 128B-swizzled UMMA layout, lo tile
+//                               right behind the hi tile)
+//   mma(acc, N, a, b, K)        producer: D[acc .. acc+N) (128 x N) = A B^T, asynchronous
+//   epilogue(acc, N, emit)      producer: waits for the GEMM; emit(row, c4, F4) per accumulator
+//                               row and 4-column group
+//   signal_ready(i) / wait_ready(i), signal_done(i) / wait_done(i)   group i handed over / retired
 // =======================================================================================
 constexpr int kTileRows = 128;                      // UMMA M
 constexpr int kATileFloats = 2 * kTileRows * 32;    // hi + lo halves of one A k-block
 OAT_FHD constexpr int b_tile_floats(int n) { return 2 * n * 32; }
 
-template <int CIN_, int HID_, int S_, int HIN_, int OR_, int ORD_, int NSEG_>
-struct ExpandDwTcBody {
-  static constexpr int CIN = CIN_, HID = HID_, S = S_, HIN = HIN_, OR = OR_, ORD = ORD_, NSEG = NSEG_;
+template <int CIN_, int HID_, int S_, int HIN_, int OR_, int NSEG_>
+struct ExpandDwPipeBody {
+  static constexpr int CIN = CIN_, HID = HID_, S = S_, HIN = HIN_, OR = OR_, NSEG = NSEG_;
   static constexpr int HOUT = (HIN - 1) / S + 1;
-  static constexpr int NR = S * (OR - 1) + 3;   // ring rows
-  static constexpr int NEW = S * OR;            // new input rows per iteration
+  static constexpr int NR = S * (OR - 1) + 3;   // rows of one depthwise window
+  static constexpr int NEW = S * OR;            // new input rows per group
   static constexpr int PRIME = NR - NEW;        // rows of the priming pass (3 - S)
+  static constexpr int RC = NR + NEW;           // ring capacity (rows)
   static constexpr int LDX = CIN + 4;
   static constexpr int LDE = HID + 4;
   static constexpr int GROUPS = (HOUT + OR - 1) / OR;
-  static constexpr int NSUB = OR / ORD;
   static_assert(PRIME >= 1 && PRIME <= NEW, "stride 1 needs OR >= 2");
-  static_assert(NEW * HIN <= kTileRows, "one iteration must fit one M=128 tile");
-  static_assert(OR % ORD == 0, "depthwise sub-passes must tile the group");
+  static_assert(NEW * HIN <= kTileRows, "one group must fit one M=128 tile");
   static_assert(CIN % 8 == 0 && CIN <= 32, "one k-block of TF32 k-slices");
   static_assert(HID % 16 == 0 && HID <= 256, "UMMA N");
   // shared-memory map (floats); operand tiles are 1024-byte aligned
@@ -479,118 +493,155 @@ struct ExpandDwTcBody {
   static constexpr int kX = kBd + HID;
   static constexpr int kXFloats = NEW * HIN * LDX;
   static constexpr int kRing = kX + 2 * kXFloats;
-  static constexpr int kSmemFloats = kRing + NR * HIN * LDE;
+  static constexpr int kSmemFloats = kRing + RC * HIN * LDE;
   static constexpr int kTmemCols = HID <= 128 ? 128 : 256;
 
   template <class X>
-  OAT_FHD static void run(X& x, const ExpandDwArgs& a, int cta) {
+  OAT_FHD static void run(X& x, const ExpandDwArgs& a, int first_unit, int unit_stride) {
     float* sm = x.smem();
-    const int nt = x.nthreads();
-    const int split = cta % a.splits;
-    const int img = cta / a.splits;  // model * B + b
-    const int model = img / a.B;
-    const float* in = a.in + (int64_t)img * HIN * HIN * CIN;
-    float* out = a.out + (int64_t)img * HOUT * HOUT * HID;
-    const int g0 = (split * GROUPS) / a.splits, g1 = ((split + 1) * GROUPS) / a.splits;
-    if (g0 >= g1) return;
     float* At = sm + kA;
     float* Bt = sm + kB;
     float* Be = sm + kBe;
     float* Wd = sm + kWd;
     float* Bd = sm + kBd;
     float* ring = sm + kRing;
-
-    auto stage = [&](int tid, int buf, int lo, int n) {
-      const int vlo = lo < 0 ? 0 : lo;
-      const int vhi = lo + n > HIN ? HIN : lo + n;
-      if (vhi <= vlo) return;
-      float* dst = sm + kX + buf * kXFloats;
-      const float* src = in + (int64_t)vlo * HIN * CIN;
-      const int chunks = (vhi - vlo) * HIN * (CIN / 4);
-      for (int i = tid; i < chunks; i += nt) {
-        const int px = i / (CIN / 4), q = i - px * (CIN / 4);
-        x.async16(dst + px * LDX + 4 * q, src + px * CIN + 4 * q);
-      }
-    };
-    auto valid_pixels = [&](int lo, int n, int* vlo_out) {
-      const int vlo = lo < 0 ? 0 : lo;
-      const int vhi = lo + n > HIN ? HIN : lo + n;
-      *vlo_out = vlo;
-      return vhi > vlo ? (vhi - vlo) * HIN : 0;
-    };
-    // rows [lo, lo+n): staged pixels -> A tile, then the expand GEMM is issued
-    auto issue = [&](int buf, int lo, int n) {
-      int vlo;
-      const int np = valid_pixels(lo, n, &vlo);
-      if (np == 0) return;
-      const float* Xs = sm + kX + buf * kXFloats;
-      x.phase_nosync([&](int tid) {
-        for (int i = tid; i < np * (CIN / 4); i += nt) {
-          const int px = i / (CIN / 4), q = i - px * (CIN / 4);
-          x.op_store4(At, kTileRows, px, 4 * q, ld4(Xs + px * LDX + 4 * q));
-        }
-      });
-      x.mma(0, HID, At, Bt, CIN);
-    };
-    // accumulator -> ring rows (bias + ReLU6); rows outside the image become zeros
-    auto collect = [&](int lo, int n) {
-      int vlo;
-      const int np = valid_pixels(lo, n, &vlo);
-      if (np > 0)
-        x.epilogue(0, HID, [&](int p, int c4, F4 v) {
-          if (p >= np) return;
-          const int r = p / HIN, col = p - r * HIN;
-          const int slot = (vlo + r) % NR;
-          const F4 b = ld4(Be + 4 * c4);
-          st4(ring + (slot * HIN + col) * LDE + 4 * c4,
-              relu6_4(F4{v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w}));
+    const int pt = x.p_threads(), ct = x.c_threads();
+    int cur_model = -1;
+    uint32_t it = 0;  // row groups handed over so far (the same count in both halves)
+    for (int unit = first_unit; unit < a.units; unit += unit_stride) {
+      const int split = unit % a.splits;
+      const int img = unit / a.splits;  // model * B + b
+      const int model = img / a.B;
+      const int g0 = (split * GROUPS) / a.splits, g1 = ((split + 1) * GROUPS) / a.splits;
+      if (g0 >= g1) continue;
+      if (model != cur_model) {
+        x.all_phase([&](int tid, int nt) {
+          const float *we = a.we.p[model], *be = a.be.p[model], *wd = a.wd.p[model], *bd = a.bd.p[model];
+          for (int i = tid; i < (CIN / 4) * HID; i += nt) {  // W_e [CIN][HID] -> weight tile rows n
+            const int n = i % HID, k4 = i / HID;
+            const F4 v{gload(we + (4 * k4 + 0) * HID + n), gload(we + (4 * k4 + 1) * HID + n),
+                       gload(we + (4 * k4 + 2) * HID + n), gload(we + (4 * k4 + 3) * HID + n)};
+            x.op_store4(Bt, HID, n, 4 * k4, v);
+          }
+          for (int i = tid; i < HID / 4; i += nt) st4(Be + 4 * i, gload4(be + 4 * i));
+          for (int i = tid; i < 9 * HID / 4; i += nt) st4(Wd + 4 * i, gload4(wd + 4 * i));
+          for (int i = tid; i < HID / 4; i += nt) st4(Bd + 4 * i, gload4(bd + 4 * i));
         });
-      x.phase([&](int tid) {
-        for (int ir = lo; ir < lo + n; ++ir) {
-          if (ir >= 0 && ir < HIN) continue;
-          float* row = ring + (((ir % NR) + NR) % NR) * HIN * LDE;
-          for (int i = tid; i < HIN * LDE / 4; i += nt) st4(row + 4 * i, zero4());
-        }
-      });
-    };
-    auto depthwise = [&](int tid, int g) {
-      dw_rows<S, ORD, NR>(ring, LDE, HIN, HOUT, Wd, Bd, HID, S * g * OR - 1, NSUB, NSEG, tid, nt,
-                          [&](int o, int oc, int c4, F4 v) {
-                            const int orow = g * OR + o;
-                            if (orow < HOUT) gstore4(out + ((int64_t)orow * HOUT + oc) * HID + 4 * c4, v);
-                          });
-    };
-
-    const int ir_first = S * g0 * OR - 1;
-    x.phase([&](int tid) {
-      const float *we = a.we.p[model], *be = a.be.p[model], *wd = a.wd.p[model], *bd = a.bd.p[model];
-      for (int i = tid; i < (CIN / 4) * HID; i += nt) {  // W_e [CIN][HID] -> weight tile rows n
-        const int n = i % HID, k4 = i / HID;
-        const F4 v{gload(we + (4 * k4 + 0) * HID + n), gload(we + (4 * k4 + 1) * HID + n),
-                   gload(we + (4 * k4 + 2) * HID + n), gload(we + (4 * k4 + 3) * HID + n)};
-        x.op_store4(Bt, HID, n, 4 * k4, v);
+        cur_model = model;
       }
-      for (int i = tid; i < HID / 4; i += nt) st4(Be + 4 * i, gload4(be + 4 * i));
-      for (int i = tid; i < 9 * HID / 4; i += nt) st4(Wd + 4 * i, gload4(wd + 4 * i));
-      for (int i = tid; i < HID / 4; i += nt) st4(Bd + 4 * i, gload4(bd + 4 * i));
-      stage(tid, 0, ir_first, PRIME);
-      stage(tid, 1, ir_first + PRIME, NEW);
-      x.async_wait();
-    });
-    issue(0, ir_first, PRIME);
-    collect(ir_first, PRIME);
-    for (int g = g0; g < g1; ++g) {
-      const int buf = (g - g0 + 1) & 1;
-      const int ir0 = S * g * OR - 1;
-      issue(buf, ir0 + PRIME, NEW);  // asynchronous: overlaps the depthwise pass below
-      x.phase([&](int tid) {
-        if (g + 1 < g1) stage(tid, buf ^ 1, ir0 + NEW + PRIME, NEW);
-        if (g > g0) depthwise(tid, g - 1);
-        x.async_wait();
-      });
-      collect(ir0 + PRIME, NEW);
+      const float* in = a.in + (int64_t)img * HIN * HIN * CIN;
+      float* out = a.out + (int64_t)img * HOUT * HOUT * HID;
+
+      // ---- producer pieces -------------------------------------------------------------
+      auto stage = [&](int tid, int buf, int lo, int n) {
+        const int vlo = lo < 0 ? 0 : lo;
+        const int vhi = lo + n > HIN ? HIN : lo + n;
+        if (vhi <= vlo) return;
+        float* dst = sm + kX + buf * kXFloats;
+        const float* src = in + (int64_t)vlo * HIN * CIN;
+        const int chunks = (vhi - vlo) * HIN * (CIN / 4);
+        for (int i = tid; i < chunks; i += pt) {
+          const int px = i / (CIN / 4), q = i - px * (CIN / 4);
+          x.async16(dst + px * LDX + 4 * q, src + px * CIN + 4 * q);
+        }
+      };
+      auto valid_pixels = [&](int lo, int n, int* vlo_out) {
+        const int vlo = lo < 0 ? 0 : lo;
+        const int vhi = lo + n > HIN ? HIN : lo + n;
+        *vlo_out = vlo;
+        return vhi > vlo ? (vhi - vlo) * HIN : 0;
+      };
+      // rows [lo, lo+n): staged pixels -> A tile, then the expand GEMM is issued
+      auto issue = [&](int buf, int lo, int n) {
+        int vlo;
+        const int np = valid_pixels(lo, n, &vlo);
+        if (np == 0) return;
+        const float* Xs = sm + kX + buf * kXFloats;
+        x.p_phase_nosync([&](int tid) {
+          for (int i = tid; i < np * (CIN / 4); i += pt) {
+            const int px = i / (CIN / 4), q = i - px * (CIN / 4);
+            x.op_store4(At, kTileRows, px, 4 * q, ld4(Xs + px * LDX + 4 * q));
+          }
+        });
+        x.mma(0, HID, At, Bt, CIN);
+      };
+      // accumulator -> ring rows (bias + ReLU6); rows outside the image become zeros
+      auto collect = [&](int lo, int n) {
+        int vlo;
+        const int np = valid_pixels(lo, n, &vlo);
+        if (np > 0)
+          x.epilogue(0, HID, [&](int p, int c4, F4 v) {
+            if (p >= np) return;
+            const int r = p / HIN, col = p - r * HIN;
+            const int slot = (vlo + r) % RC;
+            const F4 b = ld4(Be + 4 * c4);
+            st4(ring + (slot * HIN + col) * LDE + 4 * c4,
+                relu6_4(F4{v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w}));
+          });
+        x.p_phase([&](int tid) {
+          for (int ir = lo; ir < lo + n; ++ir) {
+            if (ir >= 0 && ir < HIN) continue;
+            float* row = ring + (((ir % RC) + RC) % RC) * HIN * LDE;
+            for (int i = tid; i < HIN * LDE / 4; i += pt) st4(row + 4 * i, zero4());
+          }
+          x.async_wait();
+        });
+      };
+      const int ir_first = S * g0 * OR - 1;
+      auto begin = [&]() {  // stage the priming rows and the first group; prime the ring
+        x.p_phase([&](int tid) {
+          stage(tid, 0, ir_first, PRIME);
+          stage(tid, 1, ir_first + PRIME, NEW);
+          x.async_wait();
+        });
+        issue(0, ir_first, PRIME);
+        collect(ir_first, PRIME);
+      };
+      auto produce = [&](int g, uint32_t i) {
+        const int buf = (g - g0 + 1) & 1;
+        const int ir0 = S * g * OR - 1;
+        issue(buf, ir0 + PRIME, NEW);
+        if (g + 1 < g1) x.p_phase_nosync([&](int tid) { stage(tid, buf ^ 1, ir0 + NEW + PRIME, NEW); });
+        // the new rows replace the oldest rows of the window of group i-2
+        if (X::kConcurrent && g - g0 >= 2) x.wait_done(i - 2);
+        collect(ir0 + PRIME, NEW);
+      };
+      // ---- consumer piece ----------------------------------------------------------------
+      auto depthwise = [&](int tid, int g) {
+        dw_rows<S, OR, RC>(ring, LDE, HIN, HOUT, Wd, Bd, HID, S * g * OR - 1, 1, NSEG, tid, ct,
+                           [&](int o, int oc, int c4, F4 v) {
+                             const int orow = g * OR + o;
+                             if (orow < HOUT) gstore4(out + ((int64_t)orow * HOUT + oc) * HID + 4 * c4, v);
+                           });
+      };
+
+      if (X::kConcurrent) {
+        if (x.is_producer()) {
+          if (it > 0) x.wait_done(it - 1);  // the previous unit's rows are retired
+          begin();
+          for (int g = g0; g < g1; ++g) {
+            const uint32_t i = it + (uint32_t)(g - g0);
+            produce(g, i);
+            x.signal_ready(i);
+          }
+        } else {
+          for (int g = g0; g < g1; ++g) {
+            const uint32_t i = it + (uint32_t)(g - g0);
+            x.wait_ready(i);
+            x.c_run([&](int tid) { depthwise(tid, g); });
+            x.signal_done(i);
+          }
+        }
+      } else {  // sequential executor: the producer runs one group ahead, as it may on the GPU
+        begin();
+        produce(g0, it);
+        for (int g = g0; g < g1; ++g) {
+          if (g + 1 < g1) produce(g + 1, it + (uint32_t)(g + 1 - g0));
+          x.c_run([&](int tid) { depthwise(tid, g); });
+        }
+      }
+      it += (uint32_t)(g1 - g0);
     }
-    x.phase([&](int tid) { depthwise(tid, g1 - 1); });
   }
 };
 

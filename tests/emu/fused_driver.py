@@ -26,7 +26,7 @@ def lib():
     _lib = ctypes.CDLL(LIB)
     p, i = ctypes.c_void_p, ctypes.c_int
     _lib.emu_expand_dw.argtypes = [i, p, i, p, p, p, p, p, i, i]
-    _lib.emu_expand_dw_tc.argtypes = [i, p, i, p, p, p, p, p, i, i]
+    _lib.emu_expand_dw_tc.argtypes = [i, p, i, p, p, p, p, p, i, i, i]
     _lib.emu_front.argtypes = [p, i, i, p, p, p, p, p, p, p, i, i]
   return _lib
 
@@ -64,9 +64,11 @@ def pack_stem(sd, conv, bn):
   return w.permute(2, 3, 1, 0).reshape(-1, 32).contiguous().float(), shift.float().contiguous()
 
 
-def expand_dw(idx, sd, x_nhwc, splits=2, threads=256, prefix="_encoder._model.features.", tc=False):
+def expand_dw(idx, sd, x_nhwc, splits=2, threads=256, prefix="_encoder._model.features.", tc=False,
+              ctas=3):
   """features.<idx> expand + depthwise on the host.  x_nhwc [B,H,H,cin] -> [B,Ho,Ho,hid].
-  tc=True runs the tensor-core body (its GEMM executed by plain host loops)."""
+  tc=True runs the pipelined tensor-core body (GEMM by plain host loops, `ctas` persistent
+  executors sharing the work units)."""
   p = prefix + "%d.conv" % idx
   we, be = pack_pw(sd, p + ".0.0", p + ".0.1")
   wd, bd = pack_dw(sd, p + ".1.0", p + ".1.1")
@@ -75,8 +77,11 @@ def expand_dw(idx, sd, x_nhwc, splits=2, threads=256, prefix="_encoder._model.fe
   Ho = (H - 1) // stride + 1
   x = x_nhwc.contiguous().float()
   out = torch.full((B, Ho, Ho, we.shape[1]), float("nan"))
-  fn = lib().emu_expand_dw_tc if tc else lib().emu_expand_dw
-  rc = fn(idx, _p(x), B, _p(we), _p(be), _p(wd), _p(bd), _p(out), splits, threads)
+  if tc:
+    rc = lib().emu_expand_dw_tc(idx, _p(x), B, _p(we), _p(be), _p(wd), _p(bd), _p(out), splits,
+                                threads, ctas)
+  else:
+    rc = lib().emu_expand_dw(idx, _p(x), B, _p(we), _p(be), _p(wd), _p(bd), _p(out), splits, threads)
   assert rc == 0
   return out
 

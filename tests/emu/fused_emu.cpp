@@ -34,11 +34,27 @@ struct HostExec {
   void async16(float* dst, const float* src) { memcpy(dst, src, 16); }
   void async_wait() {}
 
-  // ---- tensor-core interface, plain loops: operand tiles are [rows][32] per k-block (the lo
-  // halves stay unused), the GEMM runs when the accumulator is collected.
+  // ---- pipelined tensor-core interface as ONE sequential thread of control: the producer
+  // half has `nt` threads, the consumer half `nt` threads; operand tiles are [rows][32] per
+  // k-block (the lo halves stay unused), the GEMM runs when the accumulator is collected.
+  static constexpr bool kConcurrent = false;
+  bool is_producer() const { return true; }
+  int p_threads() const { return nt; }
+  int c_threads() const { return nt; }
   template <class F>
-  void phase_nosync(F f) { phase(f); }
-  void sync() {}
+  void all_phase(F f) {
+    for (int t = 0; t < 2 * nt; ++t) f(t, 2 * nt);
+  }
+  template <class F>
+  void p_phase(F f) { phase(f); }
+  template <class F>
+  void p_phase_nosync(F f) { phase(f); }
+  template <class F>
+  void c_run(F f) { phase(f); }
+  void signal_ready(uint32_t) {}
+  void wait_ready(uint32_t) {}
+  void signal_done(uint32_t) {}
+  void wait_done(uint32_t) {}
   void op_store4(float* tile, int /*rows*/, int row, int k, F4 v) { st4(tile + row * 32 + k, v); }
   const float *mma_a = nullptr, *mma_b = nullptr;
   int mma_k = 0, mma_n = 0, mma_acc = -1;
@@ -70,12 +86,26 @@ Weights one(const float* p) {
   return w;
 }
 
+// persistent walk: `ctas` executors share the units with a stride, like the CUDA grid
+template <class Body>
+int run_pipe(const float* in, int B, const float* we, const float* be, const float* wd,
+             const float* bd, float* out, int splits, int threads, int ctas) {
+  ExpandDwArgs a;
+  a.we = one(we); a.be = one(be); a.wd = one(wd); a.bd = one(bd);
+  a.in = in; a.out = out; a.B = B; a.splits = splits; a.units = B * splits;
+  for (int cta = 0; cta < ctas; ++cta) {
+    HostExec x(Body::kSmemFloats, threads);
+    Body::run(x, a, cta, ctas);
+  }
+  return 0;
+}
+
 template <class Body>
 int run_block(const float* in, int B, const float* we, const float* be, const float* wd,
               const float* bd, float* out, int splits, int threads) {
   ExpandDwArgs a;
   a.we = one(we); a.be = one(be); a.wd = one(wd); a.bd = one(bd);
-  a.in = in; a.out = out; a.B = B; a.splits = splits;
+  a.in = in; a.out = out; a.B = B; a.splits = splits; a.units = B * splits;
   for (int cta = 0; cta < B * splits; ++cta) {
     HostExec x(Body::kSmemFloats, threads);
     Body::run(x, a, cta);
@@ -87,13 +117,13 @@ int run_block(const float* in, int B, const float* we, const float* be, const fl
 
 extern "C" {
 
-// tensor-core bodies (host GEMM); cfg as below
+// pipelined tensor-core bodies (host GEMM, sequential producer/consumer); cfg as below
 int emu_expand_dw_tc(int cfg, const float* in, int B, const float* we, const float* be,
-                     const float* wd, const float* bd, float* out, int splits, int threads) {
+                     const float* wd, const float* bd, float* out, int splits, int threads, int ctas) {
   switch (cfg) {
-    case 2: return run_block<ExpandDwTcBody<16, 96, 2, 50, 1, 1, 21>>(in, B, we, be, wd, bd, out, splits, threads);
-    case 3: return run_block<ExpandDwTcBody<24, 144, 1, 25, 4, 2, 7>>(in, B, we, be, wd, bd, out, splits, threads);
-    case 4: return run_block<ExpandDwTcBody<24, 144, 2, 25, 2, 1, 7>>(in, B, we, be, wd, bd, out, splits, threads);
+    case 2: return run_pipe<ExpandDwPipeBody<16, 96, 2, 50, 1, 10>>(in, B, we, be, wd, bd, out, splits, threads, ctas);
+    case 3: return run_pipe<ExpandDwPipeBody<24, 144, 1, 25, 2, 7>>(in, B, we, be, wd, bd, out, splits, threads, ctas);
+    case 4: return run_pipe<ExpandDwPipeBody<24, 144, 2, 25, 1, 7>>(in, B, we, be, wd, bd, out, splits, threads, ctas);
   }
   return 1;
 }
