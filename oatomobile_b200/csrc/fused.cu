@@ -85,7 +85,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-constexpr int kPipeThreads = 512;   // warps 0-7: producer half, warps 8-15: consumer half
+#ifndef OAT_PIPE_THREADS
+#define OAT_PIPE_THREADS 512
+#endif
+constexpr int kPipeThreads = OAT_PIPE_THREADS;   // first half of the warps: producer, second half: consumer
 constexpr int kHalf = kPipeThreads / 2;
 
 // Executor of the pipelined tensor-core bodies (fused_body.h, "Executor interface").

@@ -138,9 +138,15 @@ OAT_FHD void dw_rows(const float* ring, int ld, int win, int wout, const float* 
     const int c4 = item % N4, seg = (item / N4) % nseg, sub = item / (N4 * nseg);
     const int c_lo = (seg * wout) / nseg, c_hi = ((seg + 1) * wout) / nseg;
     if (c_lo >= c_hi) continue;
+#if defined(OAT_DW_WSMEM)  // taps re-read from shared memory at every use (fewer registers)
+    const float* k = wd + 4 * c4;
+#define OAT_DW_TAP(t) ld4(k + (t) * hid)
+#else
     F4 k[9];
     OAT_FUNROLL
     for (int t = 0; t < 9; ++t) k[t] = ld4(wd + t * hid + 4 * c4);
+#define OAT_DW_TAP(t) k[t]
+#endif
     const F4 bv = ld4(bd + 4 * c4);
     const float* rowp[NW];
     OAT_FUNROLL
@@ -163,9 +169,9 @@ OAT_FHD void dw_rows(const float* ring, int ld, int win, int wout, const float* 
         F4 acc = bv;
         OAT_FUNROLL
         for (int kh = 0; kh < 3; ++kh) {
-          acc = fma4(c0[S * o + kh], k[3 * kh + 0], acc);
-          acc = fma4(c1[S * o + kh], k[3 * kh + 1], acc);
-          acc = fma4(c2[S * o + kh], k[3 * kh + 2], acc);
+          acc = fma4(c0[S * o + kh], OAT_DW_TAP(3 * kh + 0), acc);
+          acc = fma4(c1[S * o + kh], OAT_DW_TAP(3 * kh + 1), acc);
+          acc = fma4(c2[S * o + kh], OAT_DW_TAP(3 * kh + 2), acc);
         }
         emit(sub * ORD + o, oc, c4, relu6_4(acc));
       }
@@ -179,6 +185,7 @@ OAT_FHD void dw_rows(const float* ring, int ld, int win, int wout, const float* 
       }
     }
   }
+#undef OAT_DW_TAP
 }
 
 // =======================================================================================
@@ -600,6 +607,16 @@ struct ExpandDwPipeBody {
       auto produce = [&](int g, uint32_t i) {
         const int buf = (g - g0 + 1) & 1;
         const int ir0 = S * g * OR - 1;
+#if defined(OAT_ABL_NO_PRODUCE)  // timing ablation: the producer half only hands groups over
+        if (X::kConcurrent && g - g0 >= 2) x.wait_done(i - 2);
+        return;
+#endif
+#if defined(OAT_ABL_NO_GEMM)     // timing ablation: staging + zero rows only
+        if (g + 1 < g1) x.p_phase_nosync([&](int tid) { stage(tid, buf ^ 1, ir0 + NEW + PRIME, NEW); });
+        if (X::kConcurrent && g - g0 >= 2) x.wait_done(i - 2);
+        x.p_phase([&](int tid) { x.async_wait(); });
+        return;
+#endif
         issue(buf, ir0 + PRIME, NEW);
         if (g + 1 < g1) x.p_phase_nosync([&](int tid) { stage(tid, buf ^ 1, ir0 + NEW + PRIME, NEW); });
         // the new rows replace the oldest rows of the window of group i-2
@@ -608,6 +625,9 @@ struct ExpandDwPipeBody {
       };
       // ---- consumer piece ----------------------------------------------------------------
       auto depthwise = [&](int tid, int g) {
+#if defined(OAT_ABL_NO_DW)  // timing ablation: the consumer half only retires groups
+        return;
+#endif
         dw_rows<S, OR, RC>(ring, LDE, HIN, HOUT, Wd, Bd, HID, S * g * OR - 1, 1, NSEG, tid, ct,
                            [&](int o, int oc, int c4, F4 v) {
                              const int orow = g * OR + o;
