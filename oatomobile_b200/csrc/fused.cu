@@ -96,8 +96,8 @@ struct PipeExec {
   static constexpr bool kConcurrent = true;
   float* sm;        // 1024-byte aligned dynamic shared memory
   uint32_t tmem;    // TMEM base address (lane 0, first allocated column)
-  uint32_t bars;    // shared address of: [0] GEMM complete, [1,2] ready, [3,4] done (8 B each)
-  uint32_t parity;  // phase of the GEMM barrier the next epilogue waits for (producer only)
+  uint32_t bars;    // shared address of: [0,1] GEMM complete, [2,3] ready, [4,5] done (8 B each)
+  uint32_t par0, par1;  // phase of GEMM barrier 0 / 1 the next epilogue waits for (producer only)
   __device__ __forceinline__ float* smem() const { return sm; }
   __device__ __forceinline__ bool is_producer() const { return threadIdx.x < kHalf; }
   __device__ __forceinline__ int p_threads() const { return kHalf; }
@@ -122,14 +122,16 @@ struct PipeExec {
   __device__ __forceinline__ void c_run(F f) {
     f((int)threadIdx.x - kHalf);
   }
-  __device__ __forceinline__ void signal_ready(uint32_t i) { mbar_arrive(bars + 8u * (1u + (i & 1u))); }
-  __device__ __forceinline__ void wait_ready(uint32_t i) { mbar_wait(bars + 8u * (1u + (i & 1u)), (i >> 1) & 1u); }
-  __device__ __forceinline__ void signal_done(uint32_t i) { mbar_arrive(bars + 8u * (3u + (i & 1u))); }
-  __device__ __forceinline__ void wait_done(uint32_t i) { mbar_wait(bars + 8u * (3u + (i & 1u)), (i >> 1) & 1u); }
+  __device__ __forceinline__ void signal_ready(uint32_t i) { mbar_arrive(bars + 8u * (2u + (i & 1u))); }
+  __device__ __forceinline__ void wait_ready(uint32_t i) { mbar_wait(bars + 8u * (2u + (i & 1u)), (i >> 1) & 1u); }
+  __device__ __forceinline__ void signal_done(uint32_t i) { mbar_arrive(bars + 8u * (4u + (i & 1u))); }
+  __device__ __forceinline__ void wait_done(uint32_t i) { mbar_wait(bars + 8u * (4u + (i & 1u)), (i >> 1) & 1u); }
   __device__ __forceinline__ void async16(float* dst, const float* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
   }
-  __device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+  __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  __device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+  __device__ __forceinline__ void async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
   // v = 4 consecutive-k elements of operand row `row`; hi tile at `tile`, lo tile `rows`*128 B behind
   __device__ __forceinline__ void op_store4(float* tile, int rows, int row, int k, fused::F4 v) {
@@ -147,8 +149,8 @@ struct PipeExec {
   }
 
   // producer half: D[acc .. acc+N) = A B^T  (A: 128 rows, B: N rows, K-major, ceil(K/32)
-  // k-blocks; K % 8 == 0).  Asynchronous: completion is observed by epilogue().
-  __device__ __forceinline__ void mma(int acc, int N, const float* a_tile, const float* b_tile, int K) {
+  // k-blocks; K % 8 == 0).  Asynchronous: completion (barrier `buf`) is observed by epilogue().
+  __device__ __forceinline__ void mma(int buf, int acc, int N, const float* a_tile, const float* b_tile, int K) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes -> tensor core
     p_barrier();
     if (threadIdx.x == 0) {
@@ -177,17 +179,24 @@ struct PipeExec {
         const uint64_t dAh = make_desc_sw128(a0 + kb * a_kb), dBh = make_desc_sw128(b0 + kb * b_kb);
         for (int ks = 0; ks < slices; ++ks) umma_tf32(d, dAh + (uint64_t)(2 * ks), dBh + (uint64_t)(2 * ks), idesc, 1u);
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bars) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       bars + 8u * (uint32_t)buf)
+                   : "memory");
     }
   }
 
-  // producer half: emit(row, c4, F4) for accumulator row = 32*(warp%4)+lane and every other
-  // 16-column chunk (warp/4 picks the parity); a producer barrier must follow before the
-  // accumulator or the operand tiles are reused (the bodies' collect() ends with one)
+  // producer half: emit(row, c4, F4) for accumulator row = 32*(warp%4)+lane and every
+  // (kHalf/128)-th 16-column chunk; a producer barrier must follow before the accumulator or
+  // the operand tile is reused (the bodies' collect() ends with one)
   template <class Emit>
-  __device__ __forceinline__ void epilogue(int acc, int N, Emit emit) {
-    mbar_wait(bars, parity);
-    parity ^= 1u;
+  __device__ __forceinline__ void epilogue(int buf, int acc, int N, Emit emit) {
+    if (buf == 0) {
+      mbar_wait(bars, par0);
+      par0 ^= 1u;
+    } else {
+      mbar_wait(bars + 8u, par1);
+      par1 ^= 1u;
+    }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
     const int quad = warp & 3, grp = warp >> 2;
@@ -216,12 +225,13 @@ struct PipeExec {
 template <class Body>
 __global__ void __launch_bounds__(kPipeThreads, 1) expand_dw_tc_kernel(const __grid_constant__ fused::ExpandDwArgs a) {
   extern __shared__ __align__(16) uint8_t tc_smem_raw[];
-  __shared__ uint64_t bars[5];
+  __shared__ uint64_t bars[6];
   __shared__ uint32_t tmem_slot;
   const int warp = (int)threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
-    for (int i = 1; i < 5; ++i) mbar_init(smem_u32(&bars[i]), kHalf);
+    mbar_init(smem_u32(&bars[1]), 1);
+    for (int i = 2; i < 6; ++i) mbar_init(smem_u32(&bars[i]), kHalf);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {  // TMEM allocation is a warp-wide operation
@@ -234,7 +244,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) expand_dw_tc_kernel(const __g
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uintptr_t base = (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023);
-  PipeExec x{reinterpret_cast<float*>(base), tmem_slot, smem_u32(&bars[0]), 0u};
+  PipeExec x{reinterpret_cast<float*>(base), tmem_slot, smem_u32(&bars[0]), 0u, 0u};
   Body::run(x, a, (int)blockIdx.x, (int)gridDim.x);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -166,13 +166,17 @@ OAT_FHD void dw_rows(const float* ring, int ld, int win, int wout, const float* 
       ldcol(S * oc + 1, c2);
       OAT_FUNROLL
       for (int o = 0; o < ORD; ++o) {
-        F4 acc = bv;
+        F4 part[3];  // one short FMA chain per kernel row (instruction-level parallelism)
         OAT_FUNROLL
         for (int kh = 0; kh < 3; ++kh) {
-          acc = fma4(c0[S * o + kh], OAT_DW_TAP(3 * kh + 0), acc);
-          acc = fma4(c1[S * o + kh], OAT_DW_TAP(3 * kh + 1), acc);
-          acc = fma4(c2[S * o + kh], OAT_DW_TAP(3 * kh + 2), acc);
+          F4 t = kh == 0 ? bv : zero4();
+          t = fma4(c0[S * o + kh], OAT_DW_TAP(3 * kh + 0), t);
+          t = fma4(c1[S * o + kh], OAT_DW_TAP(3 * kh + 1), t);
+          t = fma4(c2[S * o + kh], OAT_DW_TAP(3 * kh + 2), t);
+          part[kh] = t;
         }
+        const F4 acc{(part[0].x + part[1].x) + part[2].x, (part[0].y + part[1].y) + part[2].y,
+                     (part[0].z + part[1].z) + part[2].z, (part[0].w + part[1].w) + part[2].w};
         emit(sub * ORD + o, oc, c4, relu6_4(acc));
       }
       if (S == 1) {
@@ -457,7 +461,7 @@ struct FrontBody {
 // walks work units (model, image, row split) with a stride and reloads weights only when
 // the model changes.
 //
-// Executor interface beyond smem()/async16()/async_wait():
+// Executor interface beyond smem()/async16():
 //   kConcurrent                 true: the two halves run concurrently (CUDA); false: one
 //                               sequential thread of control (host), producer one group ahead
 //   all_phase(f)                barrier; f(tid, nthreads) on every thread of the CTA; barrier
@@ -467,9 +471,11 @@ struct FrontBody {
 //                               [128 rows][32 k], weight tiles [N rows][32 k] per k-block (device:
 //                               TF32 hi/lo split, K-major 128B-swizzled UMMA layout, lo tile
 //                               right behind the hi tile)
-//   mma(acc, N, a, b, K)        producer: D[acc .. acc+N) (128 x N) = A B^T, asynchronous
-//   epilogue(acc, N, emit)      producer: waits for the GEMM; emit(row, c4, F4) per accumulator
+//   mma(buf, acc, N, a, b, K)   producer: D[acc .. acc+N) (128 x N) = A B^T, asynchronous; buf 0|1
+//                               names the completion barrier (two GEMMs may be in flight)
+//   epilogue(buf, acc, N, emit) producer: waits for that GEMM; emit(row, c4, F4) per accumulator
 //                               row and 4-column group
+//   async_commit(), async_wait_all(), async_wait_but_last()   cp.async group bookkeeping
 //   signal_ready(i) / wait_ready(i), signal_done(i) / wait_done(i)   group i handed over / retired
 // =======================================================================================
 constexpr int kTileRows = 128;                      // UMMA M
@@ -492,21 +498,20 @@ struct ExpandDwPipeBody {
   static_assert(CIN % 8 == 0 && CIN <= 32, "one k-block of TF32 k-slices");
   static_assert(HID % 16 == 0 && HID <= 256, "UMMA N");
   // shared-memory map (floats); operand tiles are 1024-byte aligned
-  static constexpr int kA = 0;
-  static constexpr int kB = kA + kATileFloats;
+  static constexpr int kA = 0;                                 // 2 A tiles (double-buffered GEMM)
+  static constexpr int kB = kA + 2 * kATileFloats;
   static constexpr int kBe = kB + b_tile_floats(HID);
   static constexpr int kWd = kBe + HID;
   static constexpr int kBd = kWd + 9 * HID;
-  static constexpr int kX = kBd + HID;
+  static constexpr int kX = kBd + HID;                         // 3 staging buffers (prefetch distance 2)
   static constexpr int kXFloats = NEW * HIN * LDX;
-  static constexpr int kRing = kX + 2 * kXFloats;
+  static constexpr int kRing = kX + 3 * kXFloats;
   static constexpr int kSmemFloats = kRing + RC * HIN * LDE;
-  static constexpr int kTmemCols = HID <= 128 ? 128 : 256;
+  static constexpr int kTmemCols = 2 * HID <= 128 ? 128 : (2 * HID <= 256 ? 256 : 512);
 
   template <class X>
   OAT_FHD static void run(X& x, const ExpandDwArgs& a, int first_unit, int unit_stride) {
     float* sm = x.smem();
-    float* At = sm + kA;
     float* Bt = sm + kB;
     float* Be = sm + kBe;
     float* Wd = sm + kWd;
@@ -521,14 +526,15 @@ struct ExpandDwPipeBody {
       const int model = img / a.B;
       const int g0 = (split * GROUPS) / a.splits, g1 = ((split + 1) * GROUPS) / a.splits;
       if (g0 >= g1) continue;
+      const int n = g1 - g0;
       if (model != cur_model) {
         x.all_phase([&](int tid, int nt) {
           const float *we = a.we.p[model], *be = a.be.p[model], *wd = a.wd.p[model], *bd = a.bd.p[model];
           for (int i = tid; i < (CIN / 4) * HID; i += nt) {  // W_e [CIN][HID] -> weight tile rows n
-            const int n = i % HID, k4 = i / HID;
-            const F4 v{gload(we + (4 * k4 + 0) * HID + n), gload(we + (4 * k4 + 1) * HID + n),
-                       gload(we + (4 * k4 + 2) * HID + n), gload(we + (4 * k4 + 3) * HID + n)};
-            x.op_store4(Bt, HID, n, 4 * k4, v);
+            const int nn = i % HID, k4 = i / HID;
+            const F4 v{gload(we + (4 * k4 + 0) * HID + nn), gload(we + (4 * k4 + 1) * HID + nn),
+                       gload(we + (4 * k4 + 2) * HID + nn), gload(we + (4 * k4 + 3) * HID + nn)};
+            x.op_store4(Bt, HID, nn, 4 * k4, v);
           }
           for (int i = tid; i < HID / 4; i += nt) st4(Be + 4 * i, gload4(be + 4 * i));
           for (int i = tid; i < 9 * HID / 4; i += nt) st4(Wd + 4 * i, gload4(wd + 4 * i));
@@ -539,45 +545,49 @@ struct ExpandDwPipeBody {
       const float* in = a.in + (int64_t)img * HIN * HIN * CIN;
       float* out = a.out + (int64_t)img * HOUT * HOUT * HID;
 
-      // ---- producer pieces -------------------------------------------------------------
-      auto stage = [&](int tid, int buf, int lo, int n) {
+      // Row chunk j of the unit: j = -1 the priming rows, j >= 0 the new rows of group g0+j.
+      // Its staging buffer is (j+1) % 3, its A tile / accumulator / GEMM barrier (j+1) & 1.
+      const int ir_first = S * g0 * OR - 1;
+      auto chunk_lo = [&](int j) { return j < 0 ? ir_first : ir_first + PRIME + j * NEW; };
+      auto chunk_n = [&](int j) { return j < 0 ? PRIME : NEW; };
+      auto valid_pixels = [&](int j, int* vlo_out) {
+        const int lo = chunk_lo(j), hi = lo + chunk_n(j);
         const int vlo = lo < 0 ? 0 : lo;
-        const int vhi = lo + n > HIN ? HIN : lo + n;
-        if (vhi <= vlo) return;
-        float* dst = sm + kX + buf * kXFloats;
-        const float* src = in + (int64_t)vlo * HIN * CIN;
-        const int chunks = (vhi - vlo) * HIN * (CIN / 4);
-        for (int i = tid; i < chunks; i += pt) {
-          const int px = i / (CIN / 4), q = i - px * (CIN / 4);
-          x.async16(dst + px * LDX + 4 * q, src + px * CIN + 4 * q);
-        }
-      };
-      auto valid_pixels = [&](int lo, int n, int* vlo_out) {
-        const int vlo = lo < 0 ? 0 : lo;
-        const int vhi = lo + n > HIN ? HIN : lo + n;
+        const int vhi = hi > HIN ? HIN : hi;
         *vlo_out = vlo;
         return vhi > vlo ? (vhi - vlo) * HIN : 0;
       };
-      // rows [lo, lo+n): staged pixels -> A tile, then the expand GEMM is issued
-      auto issue = [&](int buf, int lo, int n) {
+      // ---- producer pieces -------------------------------------------------------------
+      auto stage = [&](int tid, int j) {  // input rows of chunk j -> staging buffer (cp.async)
         int vlo;
-        const int np = valid_pixels(lo, n, &vlo);
+        const int np = valid_pixels(j, &vlo);
+        float* dst = sm + kX + ((j + 1) % 3) * kXFloats;
+        const float* src = in + (int64_t)vlo * HIN * CIN;
+        for (int i = tid; i < np * (CIN / 4); i += pt) {
+          const int px = i / (CIN / 4), q = i - px * (CIN / 4);
+          x.async16(dst + px * LDX + 4 * q, src + px * CIN + 4 * q);
+        }
+        x.async_commit();
+      };
+      auto issue = [&](int j) {  // staged pixels -> A tile, expand GEMM issued (asynchronous)
+        int vlo;
+        const int np = valid_pixels(j, &vlo);
         if (np == 0) return;
-        const float* Xs = sm + kX + buf * kXFloats;
+        const float* Xs = sm + kX + ((j + 1) % 3) * kXFloats;
+        float* At = sm + kA + ((j + 1) & 1) * kATileFloats;
         x.p_phase_nosync([&](int tid) {
           for (int i = tid; i < np * (CIN / 4); i += pt) {
             const int px = i / (CIN / 4), q = i - px * (CIN / 4);
             x.op_store4(At, kTileRows, px, 4 * q, ld4(Xs + px * LDX + 4 * q));
           }
         });
-        x.mma(0, HID, At, Bt, CIN);
+        x.mma((j + 1) & 1, ((j + 1) & 1) * HID, HID, At, Bt, CIN);
       };
-      // accumulator -> ring rows (bias + ReLU6); rows outside the image become zeros
-      auto collect = [&](int lo, int n) {
+      auto collect = [&](int j) {  // accumulator -> ring rows (bias + ReLU6), zeros outside the image
         int vlo;
-        const int np = valid_pixels(lo, n, &vlo);
+        const int np = valid_pixels(j, &vlo);
         if (np > 0)
-          x.epilogue(0, HID, [&](int p, int c4, F4 v) {
+          x.epilogue((j + 1) & 1, ((j + 1) & 1) * HID, HID, [&](int p, int c4, F4 v) {
             if (p >= np) return;
             const int r = p / HIN, col = p - r * HIN;
             const int slot = (vlo + r) % RC;
@@ -586,42 +596,44 @@ struct ExpandDwPipeBody {
                 relu6_4(F4{v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w}));
           });
         x.p_phase([&](int tid) {
-          for (int ir = lo; ir < lo + n; ++ir) {
+          const int lo = chunk_lo(j);
+          for (int ir = lo; ir < lo + chunk_n(j); ++ir) {
             if (ir >= 0 && ir < HIN) continue;
             float* row = ring + (((ir % RC) + RC) % RC) * HIN * LDE;
             for (int i = tid; i < HIN * LDE / 4; i += pt) st4(row + 4 * i, zero4());
           }
-          x.async_wait();
         });
       };
-      const int ir_first = S * g0 * OR - 1;
-      auto begin = [&]() {  // stage the priming rows and the first group; prime the ring
+      auto begin = [&]() {  // stage chunks -1, 0, 1; GEMMs of -1 and 0 in flight; ring primed
         x.p_phase([&](int tid) {
-          stage(tid, 0, ir_first, PRIME);
-          stage(tid, 1, ir_first + PRIME, NEW);
-          x.async_wait();
+          stage(tid, -1);
+          stage(tid, 0);
+          if (n > 1) stage(tid, 1);
+          x.async_wait_all();
         });
-        issue(0, ir_first, PRIME);
-        collect(ir_first, PRIME);
+        issue(-1);
+        issue(0);
+        collect(-1);
       };
-      auto produce = [&](int g, uint32_t i) {
-        const int buf = (g - g0 + 1) & 1;
-        const int ir0 = S * g * OR - 1;
+      auto produce = [&](int j, uint32_t i) {  // finishes group g0+j; keeps chunk j+1's GEMM in flight
 #if defined(OAT_ABL_NO_PRODUCE)  // timing ablation: the producer half only hands groups over
-        if (X::kConcurrent && g - g0 >= 2) x.wait_done(i - 2);
+        if (X::kConcurrent && j >= 2) x.wait_done(i - 2);
         return;
 #endif
-#if defined(OAT_ABL_NO_GEMM)     // timing ablation: staging + zero rows only
-        if (g + 1 < g1) x.p_phase_nosync([&](int tid) { stage(tid, buf ^ 1, ir0 + NEW + PRIME, NEW); });
-        if (X::kConcurrent && g - g0 >= 2) x.wait_done(i - 2);
-        x.p_phase([&](int tid) { x.async_wait(); });
-        return;
-#endif
-        issue(buf, ir0 + PRIME, NEW);
-        if (g + 1 < g1) x.p_phase_nosync([&](int tid) { stage(tid, buf ^ 1, ir0 + NEW + PRIME, NEW); });
-        // the new rows replace the oldest rows of the window of group i-2
-        if (X::kConcurrent && g - g0 >= 2) x.wait_done(i - 2);
-        collect(ir0 + PRIME, NEW);
+        if (j + 1 < n) {
+          x.p_phase([&](int tid) {
+            if (j + 2 < n) {
+              stage(tid, j + 2);
+              x.async_wait_but_last();  // chunk j+1 has landed, chunk j+2 may be in flight
+            } else {
+              x.async_wait_all();
+            }
+          });
+          issue(j + 1);
+        }
+        // the rows written next replace the oldest rows of the window of group i-2
+        if (X::kConcurrent && j >= 2) x.wait_done(i - 2);
+        collect(j);
       };
       // ---- consumer piece ----------------------------------------------------------------
       auto depthwise = [&](int tid, int g) {
@@ -639,28 +651,26 @@ struct ExpandDwPipeBody {
         if (x.is_producer()) {
           if (it > 0) x.wait_done(it - 1);  // the previous unit's rows are retired
           begin();
-          for (int g = g0; g < g1; ++g) {
-            const uint32_t i = it + (uint32_t)(g - g0);
-            produce(g, i);
-            x.signal_ready(i);
+          for (int j = 0; j < n; ++j) {
+            produce(j, it + (uint32_t)j);
+            x.signal_ready(it + (uint32_t)j);
           }
         } else {
-          for (int g = g0; g < g1; ++g) {
-            const uint32_t i = it + (uint32_t)(g - g0);
-            x.wait_ready(i);
-            x.c_run([&](int tid) { depthwise(tid, g); });
-            x.signal_done(i);
+          for (int j = 0; j < n; ++j) {
+            x.wait_ready(it + (uint32_t)j);
+            x.c_run([&](int tid) { depthwise(tid, g0 + j); });
+            x.signal_done(it + (uint32_t)j);
           }
         }
       } else {  // sequential executor: the producer runs one group ahead, as it may on the GPU
         begin();
-        produce(g0, it);
-        for (int g = g0; g < g1; ++g) {
-          if (g + 1 < g1) produce(g + 1, it + (uint32_t)(g + 1 - g0));
-          x.c_run([&](int tid) { depthwise(tid, g); });
+        produce(0, it);
+        for (int j = 0; j < n; ++j) {
+          if (j + 1 < n) produce(j + 1, it + (uint32_t)(j + 1));
+          x.c_run([&](int tid) { depthwise(tid, g0 + j); });
         }
       }
-      it += (uint32_t)(g1 - g0);
+      it += (uint32_t)n;
     }
   }
 };

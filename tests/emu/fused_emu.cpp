@@ -33,6 +33,9 @@ struct HostExec {
   }
   void async16(float* dst, const float* src) { memcpy(dst, src, 16); }
   void async_wait() {}
+  void async_commit() {}
+  void async_wait_all() {}
+  void async_wait_but_last() {}
 
   // ---- pipelined tensor-core interface as ONE sequential thread of control: the producer
   // half has `nt` threads, the consumer half `nt` threads; operand tiles are [rows][32] per
@@ -56,26 +59,27 @@ struct HostExec {
   void signal_done(uint32_t) {}
   void wait_done(uint32_t) {}
   void op_store4(float* tile, int /*rows*/, int row, int k, F4 v) { st4(tile + row * 32 + k, v); }
-  const float *mma_a = nullptr, *mma_b = nullptr;
-  int mma_k = 0, mma_n = 0, mma_acc = -1;
-  void mma(int acc, int N, const float* a, const float* b, int K) {
-    mma_a = a; mma_b = b; mma_k = K; mma_n = N; mma_acc = acc;
+  struct Pending { const float *a = nullptr, *b = nullptr; int k = 0, n = 0, acc = -1; } pend[2];
+  void mma(int buf, int acc, int N, const float* a, const float* b, int K) {
+    if (pend[buf].acc != -1) abort();  // the barrier of this buffer is still armed
+    pend[buf].a = a; pend[buf].b = b; pend[buf].k = K; pend[buf].n = N; pend[buf].acc = acc;
   }
   template <class Emit>
-  void epilogue(int acc, int N, Emit emit) {
-    if (acc != mma_acc || N != mma_n) abort();  // collected something that was not issued
+  void epilogue(int buf, int acc, int N, Emit emit) {
+    const Pending p = pend[buf];
+    if (acc != p.acc || N != p.n) abort();  // collected something that was not issued
     for (int row = 0; row < kTileRows; ++row)
       for (int c4 = 0; c4 < N / 4; ++c4) {
         float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        for (int k = 0; k < mma_k; ++k) {
+        for (int k = 0; k < p.k; ++k) {
           const int kb = k / 32, kk = k % 32;
-          const float av = mma_a[kb * kATileFloats + row * 32 + kk];
+          const float av = p.a[kb * kATileFloats + row * 32 + kk];
           for (int j = 0; j < 4; ++j)
-            o[j] = fmaf(av, mma_b[kb * b_tile_floats(N) + (4 * c4 + j) * 32 + kk], o[j]);
+            o[j] = fmaf(av, p.b[kb * b_tile_floats(N) + (4 * c4 + j) * 32 + kk], o[j]);
         }
         emit(row, c4, F4{o[0], o[1], o[2], o[3]});
       }
-    mma_acc = -1;
+    pend[buf].acc = -1;
   }
 };
 
