@@ -243,8 +243,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) expand_dw_tc_kernel(const __g
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uintptr_t base = (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023);
-  PipeExec x{reinterpret_cast<float*>(base), tmem_slot, smem_u32(&bars[0]), 0u, 0u};
+  // 1024-byte alignment by an offset INTO the shared array (not an integer round trip): the
+  // compiler keeps the shared address space, so the bodies' loads/stores are LDS/STS and not
+  // generic LD/ST (measured: generic accesses made this kernel latency-bound on the long scoreboard)
+  const uint32_t pad = (1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u;
+  PipeExec x{reinterpret_cast<float*>(tc_smem_raw + pad), tmem_slot, smem_u32(&bars[0]), 0u, 0u};
   Body::run(x, a, (int)blockIdx.x, (int)gridDim.x);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
