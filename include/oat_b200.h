@@ -82,9 +82,13 @@ OAT_API int oat_ensemble_set_pw_impl(OatEnsemble* ens, int32_t impl);
  * features.0 + features.1 (stem, depthwise, project) in one kernel; bits 1..3 = expand 1x1 +
  * depthwise 3x3 of features.2 / .3 / .4 in one kernel, the 6x expanded tensor staying in
  * shared memory.  Plain FP32 FMA arithmetic; results agree with the unfused path to
- * rounding.  Default: OAT_FUSE_DEFAULT, or the environment variable OAT_FUSE.        */
+ * rounding.  Default: 14 (OAT_FUSE_DEFAULT), or the environment variable OAT_FUSE.   */
 OAT_API int oat_ensemble_set_fusion(OatEnsemble* ens, int32_t mask);
 OAT_API int oat_ensemble_get_fusion(const OatEnsemble* ens);
+/* Kernel family of the fused expand+depthwise blocks when the pointwise family is tcgen05:
+ * 0 = FP32 FMA kernel, 1 = auto (default: the pipelined tcgen05 kernel for features.2, the
+ * FP32 kernel for features.3/4 — whichever measured faster on B200), 2 = tcgen05 for all. */
+OAT_API int oat_ensemble_set_fusion_tc(OatEnsemble* ens, int32_t mode);
 
 /* Selects the flow kernel family process-wide: 1 = tcgen05 3xTF32 recurrent GEMMs
  * with the state resident in shared/tensor memory (default), 0 = FP32 SIMT.        */

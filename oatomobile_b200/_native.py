@@ -27,6 +27,7 @@ SYMBOLS = (
     "oat_transform_visual_hwc", "oat_lidar_bev", "oat_trainer_create", "oat_trainer_destroy",
     "oat_train_forward_backward", "oat_adam_step", "oat_trainer_activation",
     "oat_ensemble_set_fusion", "oat_ensemble_get_fusion", "oat_debug_encoder_prefix",
+    "oat_ensemble_set_fusion_tc",
 )
 
 
@@ -86,6 +87,7 @@ def lib() -> ctypes.CDLL:
     L.oat_ensemble_set_pw_impl.argtypes = [vp, c_i32]
     L.oat_ensemble_set_fusion.argtypes = [vp, c_i32]
     L.oat_ensemble_get_fusion.argtypes = [vp]
+    L.oat_ensemble_set_fusion_tc.argtypes = [vp, c_i32]
     L.oat_debug_encoder_prefix.argtypes = [vp, vp, c_i32, c_i32, vp, vp]
     L.oat_set_flow_impl.argtypes = [c_i32]
     L.oat_plan.argtypes = [ctypes.POINTER(vp), c_i32, c_i32, vp, vp, c_i32, c_f, c_i32, c_i32, c_i32,
@@ -236,6 +238,10 @@ class EnsembleHandle:
 
   def fusion(self) -> int:
     return int(lib().oat_ensemble_get_fusion(self.ptr))
+
+  def set_fusion_tc(self, mode: int) -> None:
+    """Fused expand GEMM: 0 FP32 FMA, 1 auto (default), 2 tcgen05 for every fused block."""
+    check(lib().oat_ensemble_set_fusion_tc(self.ptr, int(mode)))
 
   def __deepcopy__(self, memo):
     return None

@@ -597,7 +597,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       f.bd = table([bi](const OatModel* m) { return m->blocks[bi].dw.b; });
       f.in = x; f.out = ens->bufH2; f.E = E; f.B = B;
       f.cin = blk.cin; f.hid = blk.hid; f.stride = blk.stride; f.hin = blk.hin;
-      f.tensor_cores = ens->pw_impl == 1 ? 1 : 0;
+      f.tensor_cores = ens->pw_impl == 1 ? ens->fuse_tc : 0;
       if (int rc = launch_fused_expand_dw(f, stream)) return rc;
       ++li;  // the expand layer's tensor-core copy is not used
     } else if (blk.hid != blk.cin) {  // expand 1x1 + BN + ReLU6

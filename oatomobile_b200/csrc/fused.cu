@@ -283,14 +283,15 @@ int allow_smem(K kernel, int bytes, int* configured) {
   return 0;
 }
 
-// CTAs per image: default 2 (tail balance vs. the rows recomputed at a split boundary);
-// OAT_FUSED_SPLITS overrides it for tuning runs.
-int splits_for(int units) {
+// Work units per image.  Measured on B200 (profiles/r1_fused_*): the FP32 kernels are fastest
+// with one CTA per image (no rows recomputed at split boundaries), the persistent tensor-core
+// kernel with two units per image (tail balance).  OAT_FUSED_SPLITS overrides both for tuning.
+int splits_for(int units, int dflt) {
   static const int env = []() {
     const char* e = getenv("OAT_FUSED_SPLITS");
     return e ? atoi(e) : 0;
   }();
-  int s = env > 0 ? env : 2;
+  int s = env > 0 ? env : dflt;
   if (s > units) s = units;
   return s < 1 ? 1 : s;
 }
@@ -306,7 +307,7 @@ int launch_tc_body(const FusedBlockLaunch& l, cudaStream_t stream) {
   fused::ExpandDwArgs a;
   a.we = table(l.we); a.be = table(l.be); a.wd = table(l.wd); a.bd = table(l.bd);
   a.in = l.in; a.out = l.out; a.B = l.B;
-  a.splits = splits_for(Body::GROUPS);
+  a.splits = splits_for(Body::GROUPS, 2);
   const int64_t units = (int64_t)l.E * l.B * a.splits;
   if (units > 0x7fffffff) return fail("fused encoder kernel: batch too large");
   a.units = (int)units;
@@ -331,7 +332,7 @@ int launch_body(const FusedBlockLaunch& l, cudaStream_t stream) {
   fused::ExpandDwArgs a;
   a.we = table(l.we); a.be = table(l.be); a.wd = table(l.wd); a.bd = table(l.bd);
   a.in = l.in; a.out = l.out; a.B = l.B;
-  a.splits = splits_for(Body::GROUPS);
+  a.splits = splits_for(Body::GROUPS, 1);
   a.units = l.E * l.B * a.splits;
   const int smem = Body::kSmemFloats * (int)sizeof(float);
   static int configured[64] = {0};
@@ -352,7 +353,9 @@ bool fused_block_supported(int cin, int hid, int stride, int hin) {
 
 int launch_fused_expand_dw(const FusedBlockLaunch& l, cudaStream_t stream) {
   if (l.E <= 0 || l.B <= 0) return 0;
-  if (l.tensor_cores) {
+  if (l.tensor_cores == 2 || (l.tensor_cores == 1 && l.hin == 50)) {
+    // tensor_cores == 1 ("auto"): the pipelined tcgen05 kernel where it measured faster than the
+    // FP32 one (features.2: 50x50 input, 100 pixels per UMMA); == 2 forces it for every shape.
     //                                          CIN  HID  S  HIN OR NSEG
     if (l.cin == 16 && l.hid == 96 && l.stride == 2 && l.hin == 50)
       return launch_tc_body<fused::ExpandDwPipeBody<16, 96, 2, 50, 1, 10>>(l, stream);
@@ -379,7 +382,7 @@ int launch_fused_front(const FusedFrontLaunch& l, cudaStream_t stream) {
   a.ws = table(l.ws); a.bs = table(l.bs); a.wd = table(l.wd); a.bd = table(l.bd);
   a.wp = table(l.wp); a.bp = table(l.bp);
   a.vis = l.visual; a.out = l.out; a.B = l.B; a.C = l.C;
-  a.splits = splits_for(fused::FrontBody::PAIRS);
+  a.splits = splits_for(fused::FrontBody::PAIRS, 1);
   const int smem = fused::FrontBody::smem_floats(l.C) * (int)sizeof(float);
   static int configured[64] = {0};
   if (int rc = allow_smem(front_kernel, smem, configured)) return rc;

@@ -20,7 +20,8 @@ struct FusedBlockLaunch {  // expand 1x1 + depthwise 3x3 of one inverted-residua
   const float* in;         // [E][B][hin][hin][cin]
   float* out;              // [E][B][hout][hout][hid]
   int E, B, cin, hid, stride, hin;
-  int tensor_cores;        // 1: expand GEMM on tcgen05 (3xTF32), 0: FP32 FMA
+  int tensor_cores;        // expand GEMM: 0 FP32 FMA kernel; 1 auto (tcgen05 3xTF32 pipelined kernel
+                           // where it is the faster one); 2 tcgen05 for every shape
 };
 bool fused_block_supported(int cin, int hid, int stride, int hin);
 int launch_fused_expand_dw(const FusedBlockLaunch& l, cudaStream_t stream);

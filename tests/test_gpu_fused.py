@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _ensemble(sds, C, mask, pw="tcgen05"):
+def _ensemble(sds, C, mask, pw="tcgen05", tc=None):
   import oatomobile_b200 as ob
   from oatomobile_b200 import _native as N
   handles = []
@@ -23,13 +23,15 @@ def _ensemble(sds, C, mask, pw="tcgen05"):
     m.load_state_dict(sd, strict=True)
     handles.append(m.to(DEV).eval())
   ens = N.EnsembleHandle([m.native_handle() for m in handles])
-  ens.set_pw_impl(pw)
+  ens.set_pw_impl("simt" if pw == "simt" else "tcgen05")
   ens.set_fusion(mask)
+  if pw == "tcgen05-all":  # pipelined tcgen05 kernel for every fused block (default: features.2 only)
+    ens.set_fusion_tc(2)
   assert ens.fusion() == mask
   return ens, handles
 
 
-@pytest.mark.parametrize("pw", ["tcgen05", "simt"])
+@pytest.mark.parametrize("pw", ["tcgen05", "tcgen05-all", "simt"])
 @pytest.mark.parametrize("C,B,E", [(4, 3, 2), (2, 1, 1), (4, 5, 3)])
 @pytest.mark.parametrize("mask", [1, 2, 4, 8, 15])
 def test_prefix_activations_match_oracle(C, B, E, mask, pw):
@@ -49,7 +51,7 @@ def test_prefix_activations_match_oracle(C, B, E, mask, pw):
       assert_close(got[m], want, 2e-5, "mask %d block %d model %d" % (mask, blocks, m))
 
 
-@pytest.mark.parametrize("pw", ["tcgen05", "simt"])
+@pytest.mark.parametrize("pw", ["tcgen05", "tcgen05-all", "simt"])
 def test_fused_z_matches_unfused_and_oracle(pw):
   from oatomobile_b200 import ops
   C, B, E = 4, 6, 2

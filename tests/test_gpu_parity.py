@@ -12,16 +12,20 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(autouse=True, params=["tcgen05", "simt", "tcgen05x2"])
+@pytest.fixture(autouse=True, params=["tcgen05", "simt", "tcgen05x2", "unfused", "fused-all"])
 def kernel_family(request):
-  """Every parity test runs on every kernel family: the tcgen05/TMA 3xTF32 path (default),
-  the FP32 SIMT path, and the tcgen05 flow with two row tiles per CTA."""
+  """Every parity test runs on every kernel family: the tcgen05/TMA 3xTF32 path, the FP32
+  SIMT path, the tcgen05 flow with two row tiles per CTA (library default), the encoder
+  without any fused block and with every fused kernel (incl. the fused stem) switched on."""
   from oatomobile_b200 import _native
-  _native.set_flow_impl(request.param)
+  flow = request.param if request.param in ("tcgen05", "simt", "tcgen05x2") else "tcgen05x2"
+  _native.set_flow_impl(flow)
   _native.set_default_pw_impl("simt" if request.param == "simt" else "tcgen05")
+  _native.set_default_fusion({"unfused": 0, "fused-all": 15}.get(request.param))
   yield request.param
   _native.set_flow_impl("tcgen05x2")  # library default
   _native.set_default_pw_impl("tcgen05")
+  _native.set_default_fusion(None)
 
 
 def _models(cfg, sds):

@@ -14,6 +14,7 @@ m.load_state_dict(synthetic_state_dict("dim", C, 50))
 m = m.to(dev).eval()
 ens = N.EnsembleHandle([m.native_handle()])
 ens.set_fusion(15)
+ens.set_fusion_tc(2)
 vis = ops.transform_visual(synthetic_inputs(1, C, 1, 4, seed=3)["lidar"].to(dev))
 out = ops.encoder_prefix(ens, vis, 4)
 torch.cuda.synchronize()
