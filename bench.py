@@ -317,7 +317,10 @@ def run_gpu_arm(args):
     peaks = _peaks()
     # dominant kernel pair: flow sample + score launches on this rank
     rows = scenes * K_SAMPLES
-    passes = e_local if grank == 0 else e_local + 1  # rank 0 scores model 0 while sampling
+    if gsize > 1 and scenes % gsize == 0:
+      passes = e_local + 1.0 / gsize  # proposals decoded for 1/R of the scenes, then E_local scoring passes
+    else:
+      passes = e_local if grank == 0 else e_local + 1  # rank 0 scores model 0 while sampling
     flow_flop = passes * rows * T_STEPS * FLOW_FLOP_PER_ROW_STEP
     flow_tflops = flow_flop / (stages["flow"] * 1e-3) / 1e12 if stages["flow"] > 0 else 0.0
     sm_mhz = clocks.get("sm_mhz") or 0

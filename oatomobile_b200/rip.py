@@ -8,11 +8,14 @@ Assembled from the reference's own primitives:
   k*    = argmin_k s ; plan = y[b, k*]
 
 Multi-GPU: the ensemble is sharded in contiguous blocks of
-E/R models per rank.  One tiny broadcast of z_0 lets every rank regenerate the
-*identical* proposals y with the (replicated, 61 KB) decoder of model 0; the only
-data-path collective is then a single all-gather of the per-model scores q
-(`[E_local,B,K]` fp32 per rank) over NCCL/NVLink.  Every rank aggregates the same
-gathered tensor, so `k*` and the plan are bit-identical on all ranks.
+E/R models per rank.  One tiny broadcast of z_0 lets every rank decode proposals with
+the (replicated, 61 KB) decoder of model 0: each rank decodes 1/R of the scenes and the
+slices are all-gathered over NVLink (rows are independent, so the gathered y is
+bit-identical to a single-GPU decode; when the scene count does not divide, every rank
+regenerates all of y instead).  Each rank then scores y under its own models and a
+single all-gather of the per-model scores q (`[E_local,B,K]` fp32 per rank) follows.
+Every rank aggregates the same gathered tensor, so `k*` and the plan are bit-identical
+on all ranks.
 """
 from typing import Dict, Optional, Sequence
 
@@ -90,12 +93,25 @@ class RIPScorer:
       # (1) z_0 from the owner of model 0 (64 floats per scene).
       z0 = z[0].contiguous() if self._rank == 0 else torch.empty_like(z[0])
       dist.broadcast(z0, src=dist.get_global_rank(self._group, 0), group=self._group)
-      if self._rank == 0:
+      Bn, Kn, Tn = x.shape[0], x.shape[1], x.shape[2]
+      if Bn % self._world == 0:
+        # (2) proposals: 1/R of the scenes per rank through the replicated decoder of model 0,
+        # all-gathered over NVLink.  Measured before (every rank but 0 decoding ALL rows, then
+        # scoring): the flow stage of ranks != 0 cost 2x rank 0's at one model per rank.
+        n = Bn // self._world
+        lo = self._rank * n
+        prop = self._models[0] if self._rank == 0 else self._proposal_model
+        y_part, _ = ops.flow_forward(prop._decoder._handle(), x[lo:lo + n].reshape(-1, Tn, 2),
+                                     z0[lo:lo + n], rows_per_z=Kn)
+        y = torch.empty_like(x)
+        dist.all_gather_into_tensor(y, y_part.view(n, Kn, Tn, 2).contiguous(), group=self._group)
+        _, q = ops.rip_sample_score(ens, z, None, goal, epsilon, proposal_idx=-1, y=y)
+      elif self._rank == 0:
         y, q = ops.rip_sample_score(ens, z, x, goal, epsilon, proposal_idx=0)
       else:
-        # (2) identical proposals, regenerated locally from the replicated decoder.
+        # (2') identical proposals, regenerated locally from the replicated decoder.
         y, _ = ops.flow_forward(self._proposal_model._decoder._handle(),
-                                x.reshape(-1, x.shape[2], 2), z0, rows_per_z=x.shape[1])
+                                x.reshape(-1, Tn, 2), z0, rows_per_z=Kn)
         y = y.view_as(x)
         _, q = ops.rip_sample_score(ens, z, None, goal, epsilon, proposal_idx=-1, y=y)
       self._mark("flow_end")
