@@ -10,11 +10,16 @@ import torch
 from oatomobile_b200 import _native as N
 
 
-def transform_visual(lidar: torch.Tensor) -> torch.Tensor:
-  """oatomobile/torch/transforms.py:34-49 — [B,C,H,W] -> [B,C,100,100] (resize + H<->W)."""
+def transform_visual(lidar: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """oatomobile/torch/transforms.py:34-49 — [B,C,H,W] -> [B,C,100,100] (resize + H<->W).
+  `out` (optional) is a preallocated contiguous float32 CUDA result buffer."""
   lidar = N.require_cuda_f32(lidar, "lidar")
   B, C, H, W = lidar.shape
-  out = torch.empty(B, C, 100, 100, device=lidar.device, dtype=torch.float32)
+  if out is None:
+    out = torch.empty(B, C, 100, 100, device=lidar.device, dtype=torch.float32)
+  elif (tuple(out.shape) != (B, C, 100, 100) or out.dtype != torch.float32 or
+        out.device != lidar.device or not out.is_contiguous()):
+    raise ValueError("`out` must be a contiguous float32 [B,C,100,100] tensor on the input's device")
   with torch.cuda.device(lidar.device):
     N.check(N.lib().oat_transform_visual(lidar.data_ptr(), B, C, H, W, out.data_ptr(),
                                          N.stream_ptr(lidar.device)))

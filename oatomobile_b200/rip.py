@@ -29,8 +29,12 @@ from oatomobile_b200.models import ImitativeModel, _CONTEXT_KEYS, _require, _sca
 class RIPScorer:
   """Scores K sampled trajectories per scene under an ensemble of ImitativeModels."""
 
+  _MAX_GRAPHS = 4          # cached encoder graphs (distinct input buffers) per scorer
+  _MAX_GRAPH_MISSES = 12   # input pointers keep changing -> graphs are switched off
+
   def __init__(self, models: Sequence[ImitativeModel], algorithm: str = "WCM",
-               group=None, proposal_model: Optional[ImitativeModel] = None) -> None:
+               group=None, proposal_model: Optional[ImitativeModel] = None,
+               use_cuda_graphs: bool = False) -> None:
     """Args:
       models: the models owned by THIS rank (all E of them on one GPU).
       algorithm: "WCM" | "MA" | "BCM", semantics as written at rip/agent.py:121-127.
@@ -38,6 +42,10 @@ class RIPScorer:
         (rank r owns global models [r*E_local, (r+1)*E_local)).
       proposal_model: on ranks that do not own global model 0, a replica of it (only
         its flow decoder is used) so proposals can be regenerated locally.
+      use_cuda_graphs: replay the ~55 launches of the encoder stage as ONE CUDA graph per set
+        of input buffers (captured on first use; callers that feed the same device buffers
+        every step, like `HostRIPPipeline`, hit the cache).  The returned `z` is then the
+        graph's static output buffer: valid until the next call with the same input buffers.
     """
     assert algorithm in ("WCM", "MA", "BCM")  # rip/agent.py:43
     self._algorithm = algorithm
@@ -53,6 +61,12 @@ class RIPScorer:
     self._ens = None
     self._ens_key = None
     self.stage_events = None  # set to a list to record (name, cuda event) marks per call
+    self._use_graphs = bool(use_cuda_graphs)
+    self._graphs = {}          # key -> (graph, z, inputs kept alive, launches per replay)
+    self._graph_misses = 0
+    self._graph_max_batch = 0
+    self._vis_buf = None
+    self.replayed_launches = 0  # kernel launches executed through graph replays
 
   def _mark(self, name: str) -> None:
     if self.stage_events is not None:
@@ -77,8 +91,55 @@ class RIPScorer:
   def encode(self, **context: torch.Tensor) -> torch.Tensor:
     """E_local x `_params` in grouped launches → z [E_local,B,64]."""
     _require(context, _CONTEXT_KEYS)
-    return ops.encode(self._ensemble(), context["visual_features"],
-                      _scalars(context, _CONTEXT_KEYS[1:]))
+    if not self._use_graphs:
+      return ops.encode(self._ensemble(), context["visual_features"],
+                        _scalars(context, _CONTEXT_KEYS[1:]))
+    return self._encode_graphed(context)
+
+  def _encode_graphed(self, context) -> torch.Tensor:
+    """The encoder stage as one CUDA-graph replay.  The graph bakes in the input pointers,
+    the ensemble's activation workspace and the TMA descriptors, so it is keyed by the input
+    buffers and dropped whenever a larger batch makes the workspace grow."""
+    ens = self._ensemble()
+    tensors = [N.require_cuda_f32(context[k], k) for k in _CONTEXT_KEYS]
+    batch = tensors[0].shape[0]
+    if batch > self._graph_max_batch:  # `oat_ensemble_reserve` reallocates: old graphs dangle
+      self._graphs.clear()
+      self._graph_max_batch = batch
+    key = (id(ens),) + tuple((t.data_ptr(), tuple(t.shape)) for t in tensors)
+    entry = self._graphs.get(key)
+    if entry is None:
+      self._graph_misses += 1
+      ctx = dict(zip(_CONTEXT_KEYS, tensors))
+      run = lambda: ops.encode(ens, ctx["visual_features"], _scalars(ctx, _CONTEXT_KEYS[1:]))
+      z = run()  # un-captured first: workspace reservation, kernel attributes, lazy init
+      if self._graph_misses > self._MAX_GRAPH_MISSES:
+        self._use_graphs = False  # the caller does not reuse its buffers: plain launches
+        self._graphs.clear()
+        return z
+      torch.cuda.current_stream(tensors[0].device).synchronize()
+      graph = torch.cuda.CUDAGraph()
+      before = N.launch_count()
+      with torch.cuda.graph(graph):
+        z = run()
+      launches = N.launch_count() - before
+      while len(self._graphs) >= self._MAX_GRAPHS:
+        self._graphs.pop(next(iter(self._graphs)))
+      entry = (graph, z, tensors, launches)
+      self._graphs[key] = entry
+    entry[0].replay()
+    self.replayed_launches += entry[3]
+    return entry[1]
+
+  def _visual_buffer(self, lidar: torch.Tensor) -> Optional[torch.Tensor]:
+    """With CUDA graphs the resized grids live in one persistent buffer per scorer (a fresh
+    tensor per call would change the encoder graph's input pointer every step)."""
+    if not self._use_graphs:
+      return None
+    shape = (lidar.shape[0], lidar.shape[1], 100, 100)
+    if self._vis_buf is None or tuple(self._vis_buf.shape) != shape or self._vis_buf.device != lidar.device:
+      self._vis_buf = torch.empty(shape, device=lidar.device, dtype=torch.float32)
+    return self._vis_buf
 
   def score(self, z: torch.Tensor, x: torch.Tensor, goal: Optional[torch.Tensor] = None,
             epsilon: float = 1.0, want_s: bool = False) -> Dict[str, torch.Tensor]:
@@ -143,11 +204,15 @@ class RIPScorer:
         import torch.distributed as dist
         lo = self._rank * (B // self._world)
         part = ops.transform_visual(lidar[lo:lo + B // self._world])
-        vis = torch.empty((B,) + tuple(part.shape[1:]), device=part.device, dtype=part.dtype)
+        vis = self._visual_buffer(lidar)
+        if vis is None:
+          vis = torch.empty((B,) + tuple(part.shape[1:]), device=part.device, dtype=part.dtype)
         dist.all_gather_into_tensor(vis, part, group=self._group)
         context["visual_features"] = vis
       else:
-        context["visual_features"] = ops.transform_visual(lidar)
+        buf = self._visual_buffer(lidar)
+        context["visual_features"] = (ops.transform_visual(lidar) if buf is None
+                                      else ops.transform_visual(lidar, out=buf))
     self._mark("encode_begin")
     z = self.encode(**context)
     self._mark("encode_end")
