@@ -18,6 +18,7 @@
 // the C+1 partial tiles in round-to-nearest fp32.  Error -> (K/8)*6e-8/C <= 1.5e-6.
 //
 // Structure (one persistent CTA per SM, 448 threads, warp-specialised):
+//   (warp numbers for the default of 4 splitter warps, -DOAT_TC_SPLIT_WARPS=n shifts the last two)
 //   warp 12  TMA producer: A tile [128 x 32] fp32 + W_hi/W_lo tiles [BN x 32] per
 //            k-block, 128B-swizzled, completion on an mbarrier (expect_tx);
 //   warps8-11 splitters: turn the raw A tile into a_hi (in place) and a_lo (second
@@ -47,7 +48,15 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // 32 fp32 = 128 B = one swizzle atom row
-constexpr int TC_THREADS = 448;  // 8 epilogue + 4 splitter warps + TMA + MMA
+#ifndef OAT_TC_SPLIT_WARPS
+#define OAT_TC_SPLIT_WARPS 4
+#endif
+constexpr int TC_SPLIT_WARPS = OAT_TC_SPLIT_WARPS;       // warps 8 .. 8+TC_SPLIT_WARPS-1
+constexpr int TC_SPLIT_THREADS = 32 * TC_SPLIT_WARPS;
+constexpr int TC_TMA_WARP = 8 + TC_SPLIT_WARPS;
+constexpr int TC_MMA_WARP = 9 + TC_SPLIT_WARPS;
+constexpr int TC_THREADS = 32 * (10 + TC_SPLIT_WARPS);  // 8 epilogue + splitter warps + TMA + MMA
+static_assert((TC_BM * TC_BK / 4) % TC_SPLIT_THREADS == 0, "splitters must tile the A tile");
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_MAX_STAGES = 5;
 constexpr int TC_TMEM_COLS = 512;
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_split(s), 128);
+      mbar_init(bar_split(s), TC_SPLIT_THREADS);
       mbar_init(bar_empty(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -208,14 +217,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
     mbar_init(bar_wfree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 13) {  // TMEM allocation is a warp-wide operation
+  if (warp == TC_MMA_WARP) {  // TMEM allocation is a warp-wide operation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_base_slot)),
                  "r"(TC_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == 12 && lane == 0) {
+  if (warp == TC_TMA_WARP && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapWh)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapWl)) : "memory");
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
   const int tiles_per_model = a.m_tiles * a.n_tiles;
   const int num_tiles = tiles_per_model * a.E;
 
-  if (warp == 12) {
+  if (warp == TC_TMA_WARP) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0, wgen = 0;
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
         }
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == TC_MMA_WARP) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = BN
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
       }
     }
   } else if (warp >= 8) {
-    // ===================== splitters (128 threads) =====================
+    // ===================== splitters =====================
     const int st = threadIdx.x - 256;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -322,8 +331,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
         mbar_wait(bar_full(s), ph);
         const uint32_t pa = sA(s), pl = sAl(s);
 #pragma unroll
-        for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
-          const uint32_t off = (uint32_t)(st + i * 128) * 16u;
+        for (int i = 0; i < TC_A_BYTES / 16 / TC_SPLIT_THREADS; ++i) {
+          const uint32_t off = (uint32_t)(st + i * TC_SPLIT_THREADS) * 16u;
           uint32_t x, y, z, w;
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                        : "=r"(x), "=r"(y), "=r"(z), "=r"(w)
@@ -334,9 +343,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
           const uint32_t ly = __float_as_uint(__uint_as_float(y) - __uint_as_float(hy)) & 0xffffe000u;
           const uint32_t lz = __float_as_uint(__uint_as_float(z) - __uint_as_float(hz)) & 0xffffe000u;
           const uint32_t lw = __float_as_uint(__uint_as_float(w) - __uint_as_float(hw)) & 0xffffe000u;
+#if !defined(OAT_TC_NO_HI_STORE)
+          // (-DOAT_TC_NO_HI_STORE: experiment that leaves the raw fp32 tile as the hi operand,
+          // relying on kind::tf32 ignoring the 13 low mantissa bits)
           asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(pa + off), "r"(hx), "r"(hy),
                        "r"(hz), "r"(hw)
                        : "memory");
+#endif
           asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(pl + off), "r"(lx), "r"(ly),
                        "r"(lz), "r"(lw)
                        : "memory");
@@ -440,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 13) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(TC_TMEM_COLS)
