@@ -7,9 +7,9 @@ from oatomobile_b200 import _native
 from oatomobile_b200.rip import RIPScorer
 from oatomobile_b200.synthetic import synthetic_inputs, synthetic_state_dict
 
-which = sys.argv[1] if len(sys.argv) > 1 else "tcgen05"
+which = sys.argv[1] if len(sys.argv) > 1 else "tcgen05x2"  # simt | tcgen05 | tcgen05x2 (library default)
 _native.set_flow_impl(which)
-_native.set_default_pw_impl(which)
+_native.set_default_pw_impl("simt" if which == "simt" else "tcgen05")
 dev = "cuda:0"
 B, C, E, K, T = 3, 4, 2, 96, 10
 inp = synthetic_inputs(B, C, K, T, seed=3)
