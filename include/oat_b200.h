@@ -81,7 +81,8 @@ OAT_API int oat_ensemble_set_pw_impl(OatEnsemble* ens, int32_t impl);
 /* Selects which of the encoder's first blocks run as fused kernels (fused.cu): bit 0 =
  * features.0 + features.1 (stem, depthwise, project) in one kernel; bits 1..3 = expand 1x1 +
  * depthwise 3x3 of features.2 / .3 / .4 in one kernel, the 6x expanded tensor staying in
- * shared memory.  Plain FP32 FMA arithmetic; results agree with the unfused path to
+ * shared memory; bit 4 = depthwise 3x3 + project of features.1 in one kernel (ignored when
+ * bit 0 is set).  Plain FP32 FMA arithmetic; results agree with the unfused path to
  * rounding.  Default: 14 (OAT_FUSE_DEFAULT), or the environment variable OAT_FUSE.   */
 OAT_API int oat_ensemble_set_fusion(OatEnsemble* ens, int32_t mask);
 OAT_API int oat_ensemble_get_fusion(const OatEnsemble* ens);

@@ -138,8 +138,8 @@ def set_default_fusion(mask) -> None:
   """Fusion mask (see `oat_ensemble_set_fusion`) for ensembles created from now on;
   None restores the library default."""
   global _default_fusion
-  if mask is not None and not 0 <= int(mask) <= 15:
-    raise ValueError("fusion mask must be in [0, 15]")
+  if mask is not None and not 0 <= int(mask) <= 31:
+    raise ValueError("fusion mask must be in [0, 31]")
   _default_fusion = None if mask is None else int(mask)
 
 
@@ -233,7 +233,8 @@ class EnsembleHandle:
     check(lib().oat_ensemble_set_pw_impl(self.ptr, {"simt": 0, "tcgen05": 1}[impl]))
 
   def set_fusion(self, mask: int) -> None:
-    """Bit 0: features.0+1 as one kernel; bits 1-3: expand+depthwise of features.2-4 fused."""
+    """Bit 0: features.0+1 as one kernel; bits 1-3: expand+depthwise of features.2-4 fused;
+    bit 4: depthwise+project of features.1 fused."""
     check(lib().oat_ensemble_set_fusion(self.ptr, int(mask)))
 
   def fusion(self) -> int:

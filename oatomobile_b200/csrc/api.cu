@@ -350,7 +350,7 @@ int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble
 #define OAT_FUSE_DEFAULT 14
 #endif
   e->fuse = OAT_FUSE_DEFAULT;
-  if (const char* env = getenv("OAT_FUSE")) e->fuse = atoi(env) & 15;
+  if (const char* env = getenv("OAT_FUSE")) e->fuse = atoi(env) & 31;
   if (const char* env = getenv("OAT_FUSE_TC")) e->fuse_tc = atoi(env) < 0 ? 0 : (atoi(env) > 2 ? 2 : atoi(env));
   // ---- tensor-core copies of every pointwise layer: [E][N][K], TF32 hi/lo split ----
   {
@@ -423,7 +423,7 @@ int oat_ensemble_set_pw_impl(OatEnsemble* ens, int32_t impl) {
 
 int oat_ensemble_set_fusion(OatEnsemble* ens, int32_t mask) {
   if (!ens) return fail("oat_ensemble_set_fusion: null ensemble");
-  if (mask < 0 || mask > 15) return fail("oat_ensemble_set_fusion: mask must be in [0, 15]");
+  if (mask < 0 || mask > 31) return fail("oat_ensemble_set_fusion: mask must be in [0, 31]");
   ens->fuse = mask;
   return 0;
 }

@@ -104,7 +104,8 @@ struct OatEnsemble {
   float* tc_arena = nullptr;
   int pw_impl = 1;               // 1 = tcgen05 3xTF32 (default), 0 = FP32 SIMT
   int fuse = 0;                  // bit 0: features.0+1 in one kernel; bits 1-3: expand+depthwise
-                                 // of features.2-4 in one kernel (fused.cu)
+                                 // of features.2-4 in one kernel; bit 4: depthwise+project of
+                                 // features.1 in one kernel (ignored with bit 0) (fused.cu)
   int fuse_tc = 1;               // fused expand GEMM with pw_impl == 1: 1 auto, 2 tcgen05 always, 0 FP32
   int device = 0;
   int reserved_batch = 0;

@@ -270,6 +270,24 @@ __global__ void __launch_bounds__(kFusedThreads, 2) front_kernel(const __grid_co
   fused::FrontBody::run(x, a, (int)blockIdx.x);
 }
 
+constexpr int kDwProjectThreads = 128;
+struct SmallExec {  // same interface as CudaExec for a 128-thread CTA
+  float* sm;
+  __device__ __forceinline__ float* smem() const { return sm; }
+  __device__ __forceinline__ int nthreads() const { return kDwProjectThreads; }
+  template <class F>
+  __device__ __forceinline__ void phase(F f) {
+    f((int)threadIdx.x);
+    __syncthreads();
+  }
+};
+
+__global__ void __launch_bounds__(kDwProjectThreads, 6) dw_project_kernel(const __grid_constant__ fused::DwProjectArgs a) {
+  __shared__ __align__(16) float dwp_smem[fused::DwProjectBody::kSmemFloats];
+  SmallExec x{dwp_smem};
+  fused::DwProjectBody::run(x, a, (int)blockIdx.x);
+}
+
 // opt in to > 48 KB of dynamic shared memory, once per (kernel, device)
 template <class K>
 int allow_smem(K kernel, int bytes, int* configured) {
@@ -373,6 +391,18 @@ int launch_fused_expand_dw(const FusedBlockLaunch& l, cudaStream_t stream) {
   if (l.cin == 24 && l.hid == 144 && l.stride == 2 && l.hin == 25)
     return launch_body<fused::ExpandDwBody<24, 144, 2, 25, 1, 8, 7>>(l, stream);
   return fail("launch_fused_expand_dw: unsupported block shape");
+}
+
+int launch_fused_dw_project(const FusedDwProjectLaunch& l, cudaStream_t stream) {
+  if (l.E <= 0 || l.B <= 0) return 0;
+  fused::DwProjectArgs a;
+  a.wd = table(l.wd); a.bd = table(l.bd); a.wp = table(l.wp); a.bp = table(l.bp);
+  a.in = l.in; a.out = l.out; a.B = l.B;
+  const int64_t ctas = (int64_t)l.E * l.B * fused::DwProjectBody::PAIRS;
+  if (ctas > 0x7fffffff) return fail("fused encoder kernel: batch too large");
+  dw_project_kernel<<<(unsigned)ctas, kDwProjectThreads, 0, stream>>>(a);
+  OAT_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_fused_front(const FusedFrontLaunch& l, cudaStream_t stream) {

@@ -14,6 +14,15 @@ struct FusedFrontLaunch {  // features.0 + features.1 in one kernel
 };
 int launch_fused_front(const FusedFrontLaunch& l, cudaStream_t stream);
 
+struct FusedDwProjectLaunch {  // features.1: depthwise 3x3 + project 32->16 in one kernel
+  PtrTable wd, bd;             // depthwise [9][32], [32]
+  PtrTable wp, bp;             // project [32][16], [16]
+  const float* in;             // [E][B][50][50][32] (stem output)
+  float* out;                  // [E][B][50][50][16]
+  int E, B;
+};
+int launch_fused_dw_project(const FusedDwProjectLaunch& l, cudaStream_t stream);
+
 struct FusedBlockLaunch {  // expand 1x1 + depthwise 3x3 of one inverted-residual block
   PtrTable we, be;         // expand [cin][hid], [hid]
   PtrTable wd, bd;         // depthwise [9][hid], [hid]

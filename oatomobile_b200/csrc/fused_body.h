@@ -129,7 +129,11 @@ OAT_FHD void gemm_rows(const float* A, int lda, const float* W, int ldw, const f
 // slides along the segment in registers.  wd: [9][hid] (tap-major), bd: [hid], shared memory.
 // emit(o, oc, c4, v): o-th output row of the call, column oc.
 // ---------------------------------------------------------------------------------------
-template <int S, int ORD, int RING, class Emit>
+// GLOBAL = true: `ring` is the whole image in global memory ([RING = hin rows][win][ld]); rows
+// outside it read as zeros and loads go through the read-only path.
+// WSMEM = true: the 9 taps are re-read from shared memory at every use instead of living in 36
+// registers (for small CTAs whose occupancy is register-bound).
+template <int S, int ORD, int RING, bool GLOBAL = false, bool WSMEM = false, class Emit>
 OAT_FHD void dw_rows(const float* ring, int ld, int win, int wout, const float* wd, const float* bd,
                      int hid, int ir0, int nsub, int nseg, int tid, int nthreads, Emit emit) {
   constexpr int NW = S * (ORD - 1) + 3;
@@ -138,27 +142,29 @@ OAT_FHD void dw_rows(const float* ring, int ld, int win, int wout, const float* 
     const int c4 = item % N4, seg = (item / N4) % nseg, sub = item / (N4 * nseg);
     const int c_lo = (seg * wout) / nseg, c_hi = ((seg + 1) * wout) / nseg;
     if (c_lo >= c_hi) continue;
-#if defined(OAT_DW_WSMEM)  // taps re-read from shared memory at every use (fewer registers)
-    const float* k = wd + 4 * c4;
-#define OAT_DW_TAP(t) ld4(k + (t) * hid)
-#else
-    F4 k[9];
-    OAT_FUNROLL
-    for (int t = 0; t < 9; ++t) k[t] = ld4(wd + t * hid + 4 * c4);
-#define OAT_DW_TAP(t) k[t]
-#endif
+    F4 k[WSMEM ? 1 : 9];
+    if (!WSMEM) {
+      OAT_FUNROLL
+      for (int t = 0; t < (WSMEM ? 1 : 9); ++t) k[t] = ld4(wd + t * hid + 4 * c4);
+    }
+    const float* kp = wd + 4 * c4;
+#define OAT_DW_TAP(t) (WSMEM ? ld4(kp + (t) * hid) : k[WSMEM ? 0 : (t)])
     const F4 bv = ld4(bd + 4 * c4);
     const float* rowp[NW];
+    bool rowok[NW];
     OAT_FUNROLL
     for (int r = 0; r < NW; ++r) {
-      const int slot = ((ir0 + sub * S * ORD + r) % RING + RING) % RING;
+      const int ir = ir0 + sub * S * ORD + r;
+      const int slot = (ir % RING + RING) % RING;
+      rowok[r] = !GLOBAL || (ir >= 0 && ir < RING);
       rowp[r] = ring + (slot * win) * ld + 4 * c4;
     }
     F4 c0[NW], c1[NW], c2[NW];
     auto ldcol = [&](int ic, F4(&col)[NW]) {
       const bool ok = ic >= 0 && ic < win;
       OAT_FUNROLL
-      for (int r = 0; r < NW; ++r) col[r] = ok ? ld4(rowp[r] + ic * ld) : zero4();
+      for (int r = 0; r < NW; ++r)
+        col[r] = (ok && rowok[r]) ? (GLOBAL ? gload4(rowp[r] + ic * ld) : ld4(rowp[r] + ic * ld)) : zero4();
     };
     ldcol(S * c_lo - 1, c0);
     ldcol(S * c_lo, c1);
@@ -446,6 +452,64 @@ struct FrontBody {
   }
 };
 
+
+// =======================================================================================
+// DwProjectBody: features.1 after the stem — depthwise 3x3 (32 ch, stride 1, +BN+ReLU6) and
+// project 1x1 32->16 (+BN) in one kernel.  in [E][B][50][50][32] -> out [E][B][50][50][16].
+// Small CTAs (one pair of output rows each, 16 KB of shared memory) instead of a ring: the
+// depthwise window slides over the input rows in global memory / L2, its output goes to shared
+// memory, the project GEMM reads it from there.  Many CTAs per SM hide the two barriers.
+// =======================================================================================
+struct DwProjectArgs {
+  Weights wd, bd;  // depthwise [9][32] + [32]
+  Weights wp, bp;  // project [32][16] + [16]
+  const float* in;
+  float* out;
+  int B;
+};
+
+struct DwProjectBody {
+  static constexpr int H = 50, CH = 32, CO = 16, LDD = CH + 4;
+  static constexpr int PAIRS = H / 2;  // CTAs per image
+  static constexpr int kWd = 0;
+  static constexpr int kBd = kWd + 9 * CH;
+  static constexpr int kWp = kBd + CH;
+  static constexpr int kBp = kWp + CH * CO;
+  static constexpr int kD = kBp + CO;              // [2*50][36]
+  static constexpr int kSmemFloats = kD + 2 * H * LDD;
+
+  template <class X>
+  OAT_FHD static void run(X& x, const DwProjectArgs& a, int cta) {
+    float* sm = x.smem();
+    const int nt = x.nthreads();
+    const int pair = cta % PAIRS;
+    const int img = cta / PAIRS;  // model * B + b
+    const int model = img / a.B;
+    const float* in = a.in + (int64_t)img * H * H * CH;
+    float* out = a.out + ((int64_t)img * H + 2 * pair) * H * CO;
+    float* Wd = sm + kWd;
+    float* Bd = sm + kBd;
+    float* Wp = sm + kWp;
+    float* Bp = sm + kBp;
+    float* D = sm + kD;
+    x.phase([&](int tid) {
+      const float *wd = a.wd.p[model], *bd = a.bd.p[model], *wp = a.wp.p[model], *bp = a.bp.p[model];
+      for (int i = tid; i < 9 * CH / 4; i += nt) st4(Wd + 4 * i, gload4(wd + 4 * i));
+      for (int i = tid; i < CH / 4; i += nt) st4(Bd + 4 * i, gload4(bd + 4 * i));
+      for (int i = tid; i < CH * CO / 4; i += nt) st4(Wp + 4 * i, gload4(wp + 4 * i));
+      for (int i = tid; i < CO / 4; i += nt) st4(Bp + 4 * i, gload4(bp + 4 * i));
+    });
+    x.phase([&](int tid) {
+      dw_rows<1, 2, H, true, true>(in, CH, H, H, Wd, Bd, CH, 2 * pair - 1, 1, 16, tid, nt,
+                             [&](int o, int oc, int c4, F4 v) { st4(D + (o * H + oc) * LDD + 4 * c4, v); });
+    });
+    x.phase([&](int tid) {
+      gemm_rows<4>(D, LDD, Wp, CO, Bp, 2 * H, CH, CO / 4, tid, nt, [&](int q, int c4, F4 v) {
+        gstore4(out + (int64_t)q * CO + 4 * c4, v);
+      });
+    });
+  }
+};
 
 // =======================================================================================
 // Tensor-core, pipelined variant (the default on the GPU).

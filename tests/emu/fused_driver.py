@@ -28,6 +28,7 @@ def lib():
     _lib.emu_expand_dw.argtypes = [i, p, i, p, p, p, p, p, i, i]
     _lib.emu_expand_dw_tc.argtypes = [i, p, i, p, p, p, p, p, i, i, i]
     _lib.emu_front.argtypes = [p, i, i, p, p, p, p, p, p, p, i, i]
+    _lib.emu_dw_project.argtypes = [p, i, p, p, p, p, p, i]
   return _lib
 
 
@@ -95,5 +96,17 @@ def front(sd, visual, splits=2, threads=256, prefix="_encoder._model.features.")
   v = visual.contiguous().float()
   out = torch.full((B, 50, 50, 16), float("nan"))
   rc = lib().emu_front(_p(v), B, C, _p(ws), _p(bs), _p(wd), _p(bd), _p(wp), _p(bp), _p(out), splits, threads)
+  assert rc == 0
+  return out
+
+
+def dw_project(sd, x_nhwc, threads=128, prefix="_encoder._model.features."):
+  """features.1 (depthwise + project) on the host.  x_nhwc [B,50,50,32] -> [B,50,50,16]."""
+  wd, bd = pack_dw(sd, prefix + "1.conv.0.0", prefix + "1.conv.0.1")
+  wp, bp = pack_pw(sd, prefix + "1.conv.1", prefix + "1.conv.2")
+  x = x_nhwc.contiguous().float()
+  B = x.shape[0]
+  out = torch.full((B, 50, 50, 16), float("nan"))
+  rc = lib().emu_dw_project(_p(x), B, _p(wd), _p(bd), _p(wp), _p(bp), _p(out), threads)
   assert rc == 0
   return out

@@ -143,6 +143,18 @@ int emu_expand_dw(int cfg, const float* in, int B, const float* we, const float*
   return 1;
 }
 
+int emu_dw_project(const float* in, int B, const float* wd, const float* bd, const float* wp,
+                   const float* bp, float* out, int threads) {
+  DwProjectArgs a;
+  a.wd = one(wd); a.bd = one(bd); a.wp = one(wp); a.bp = one(bp);
+  a.in = in; a.out = out; a.B = B;
+  for (int cta = 0; cta < B * DwProjectBody::PAIRS; ++cta) {
+    HostExec x(DwProjectBody::kSmemFloats, threads);
+    DwProjectBody::run(x, a, cta);
+  }
+  return 0;
+}
+
 int emu_front(const float* vis, int B, int C, const float* ws, const float* bs, const float* wd,
               const float* bd, const float* wp, const float* bp, float* out, int splits, int threads) {
   FrontArgs a;

@@ -78,3 +78,12 @@ def test_expand_dw_matches_oracle(case, idx, splits, threads, tc):
   want = acts["dw%d" % idx].permute(0, 2, 3, 1)
   assert got.shape == want.shape
   assert _err(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("threads", [128, 37])
+def test_dw_project_matches_oracle(case, threads):
+  sd, _, acts = case
+  x = acts["stem"].permute(0, 2, 3, 1).contiguous()
+  got = FD.dw_project(sd, x, threads=threads)
+  assert not torch.isnan(got).any()
+  assert _err(got, acts["out1"].permute(0, 2, 3, 1)) < 2e-5

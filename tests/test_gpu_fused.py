@@ -33,7 +33,7 @@ def _ensemble(sds, C, mask, pw="tcgen05", tc=None):
 
 @pytest.mark.parametrize("pw", ["tcgen05", "tcgen05-all", "simt"])
 @pytest.mark.parametrize("C,B,E", [(4, 3, 2), (2, 1, 1), (4, 5, 3)])
-@pytest.mark.parametrize("mask", [1, 2, 4, 8, 15])
+@pytest.mark.parametrize("mask", [1, 2, 4, 8, 15, 16, 30])
 def test_prefix_activations_match_oracle(C, B, E, mask, pw):
   """Activation after blocks 1..4 with each fused kernel switched on alone and all together,
   with the fused pointwise GEMMs on the tensor cores (3xTF32) and as FP32 FMAs."""
@@ -60,7 +60,7 @@ def test_fused_z_matches_unfused_and_oracle(pw):
   visual = R.transform_visual(inp["lidar"])
   scalars = torch.cat([inp["velocity"], inp["is_at_traffic_light"], inp["traffic_light_state"]], 1)
   zs = {}
-  for mask in (0, 15):
+  for mask in (0, 15, 30):
     ens, keep = _ensemble(sds, C, mask, pw)
     zs[mask] = ops.encode(ens, visual.to(DEV), scalars.to(DEV)).cpu()
   with torch.no_grad():
@@ -69,7 +69,9 @@ def test_fused_z_matches_unfused_and_oracle(pw):
                                 inp["traffic_light_state"])
       assert_close(zs[15][m], want, REL_TOL, "fused z[%d]" % m)
       assert_close(zs[0][m], want, REL_TOL, "unfused z[%d]" % m)
+      assert_close(zs[30][m], want, REL_TOL, "fused (mask 30) z[%d]" % m)
   assert_close(zs[15], zs[0], 5e-5, "fused vs unfused z")
+  assert_close(zs[30], zs[0], 5e-5, "fused (mask 30) vs unfused z")
 
 
 def test_fused_full_batch_determinism_and_subset():
@@ -95,3 +97,18 @@ def test_fused_full_batch_determinism_and_subset():
       want = R.imitative_params(sds[m], visual[sub], inp["velocity"][sub],
                                 inp["is_at_traffic_light"][sub], inp["traffic_light_state"][sub])
       assert_close(z1[m, sub], want, REL_TOL, "z[%d]" % m)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 4, 200, 200), (2, 2, 200, 200), (1, 3, 37, 201), (2, 1, 120, 64),
+                                     (1, 2, 400, 400)])
+def test_tiled_transform_is_bit_identical_to_the_gather_kernel(B, C, H, W):
+  """`transform_visual_tiled_kernel` (NCHW, shared-memory staged) against the direct-gather
+  kernel (reached through the HWC entry point on the permuted input) and the oracle
+  (transforms.py:34-49); 400x400 exceeds the staged window and takes the gather kernel."""
+  from oatomobile_b200 import ops
+  g = torch.Generator().manual_seed(H * 1000 + W)
+  lidar = torch.rand(B, C, H, W, generator=g)
+  got = ops.transform_visual(lidar.to(DEV))
+  ref = ops.transform_visual_hwc(lidar.permute(0, 2, 3, 1).contiguous().to(DEV))
+  assert torch.equal(got, ref)
+  assert_close(got, R.transform_visual(lidar), 1e-6, "transform")
