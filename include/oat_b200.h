@@ -83,7 +83,7 @@ OAT_API int oat_ensemble_set_pw_impl(OatEnsemble* ens, int32_t impl);
  * depthwise 3x3 of features.2 / .3 / .4 in one kernel, the 6x expanded tensor staying in
  * shared memory; bit 4 = depthwise 3x3 + project of features.1 in one kernel (ignored when
  * bit 0 is set).  Plain FP32 FMA arithmetic; results agree with the unfused path to
- * rounding.  Default: 14 (OAT_FUSE_DEFAULT), or the environment variable OAT_FUSE.   */
+ * rounding.  Default: 30 (OAT_FUSE_DEFAULT), or the environment variable OAT_FUSE.   */
 OAT_API int oat_ensemble_set_fusion(OatEnsemble* ens, int32_t mask);
 OAT_API int oat_ensemble_get_fusion(const OatEnsemble* ens);
 /* Kernel family of the fused expand+depthwise blocks when the pointwise family is tcgen05:

@@ -343,11 +343,11 @@ int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble
     e->models.push_back(models[i]);
   }
   e->device = models[0]->device;
-  // Default: expand+depthwise of features.2-4 fused (measured -0.2 ms of 4.46 ms per encode at
-  // B=256, E=4); the fused features.0+1 kernel is correct but not faster than the separate
-  // launches yet, so bit 0 stays off.
+  // Default: depthwise+project of features.1 and expand+depthwise of features.2-4 fused
+  // (measured 4.47 -> 4.21 ms per encode at B=256, E=4); the fused features.0+1 kernel is
+  // correct but not faster than the separate launches, so bit 0 stays off.
 #ifndef OAT_FUSE_DEFAULT
-#define OAT_FUSE_DEFAULT 14
+#define OAT_FUSE_DEFAULT 30
 #endif
   e->fuse = OAT_FUSE_DEFAULT;
   if (const char* env = getenv("OAT_FUSE")) e->fuse = atoi(env) & 31;
