@@ -120,8 +120,14 @@ class RIPScorer:
       torch.cuda.current_stream(tensors[0].device).synchronize()
       graph = torch.cuda.CUDAGraph()
       before = N.launch_count()
-      with torch.cuda.graph(graph):
-        z = run()
+      try:
+        with torch.cuda.graph(graph):
+          z = run()
+      except Exception:  # capture not possible here (e.g. a foreign capture in progress):
+        self._use_graphs = False  # keep working with one launch per kernel
+        self._graphs.clear()
+        torch.cuda.synchronize(tensors[0].device)
+        return run()
       launches = N.launch_count() - before
       while len(self._graphs) >= self._MAX_GRAPHS:
         self._graphs.pop(next(iter(self._graphs)))
