@@ -177,6 +177,8 @@ int launch_aggregate(const float* q, int E, int B, int K, int algo, const float*
                      float* s, int32_t* kstar, float* sbest, float* plan,
                      cudaStream_t stream);
 
+int simt_pw_gemm(const float* A, const float* W_kn, const float* bias, const float* R, float* C,
+                 int M, int K, int N, int relu6, cudaStream_t stream);
 int launch_transform_visual(const float* lidar, int B, int C, int H, int W, float* visual,
                             cudaStream_t stream, bool hwc = false);
 

@@ -547,6 +547,19 @@ __global__ void __launch_bounds__(64) merger_kernel(const __grid_constant__ Merg
 
 }  // namespace
 
+// FP32 shared-memory tiled GEMM for one model: C[M][N] = A[M][K] W[K][N] + bias (+ R), used by
+// the training step (train.cu) for the pointwise forward and input-gradient products.
+int simt_pw_gemm(const float* A, const float* W_kn, const float* bias, const float* R, float* C,
+                 int M, int K, int N, int relu6, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  PwArgs a;
+  for (int e = 0; e < kMaxModels; ++e) { a.w.p[e] = nullptr; a.bias.p[e] = nullptr; }
+  a.w.p[0] = W_kn; a.bias.p[0] = bias;
+  a.A = A; a.C = C; a.R = R; a.a_stride = 0; a.c_stride = 0;
+  a.M = M; a.K = K; a.N = N; a.relu6 = relu6;
+  return launch_pw(a, 1, stream, nullptr);
+}
+
 int launch_transform_visual(const float* lidar, int B, int C, int H, int W, float* visual,
                             cudaStream_t stream, bool hwc) {
   if (B <= 0) return 0;

@@ -9,6 +9,7 @@
 // backward over a handful of rows is badly conditioned — see DESIGN.md §9); the
 // tensor-core / fused-block treatment the inference path received comes next.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "train_impl.h"
@@ -37,9 +38,73 @@ struct BlockSize<train::CilL1Step> {
   static constexpr int value = 32;
 };
 
+// W [N][K] (reference layout, changes every step) -> W^T [K][N] for the tiled GEMM's B operand
+__global__ void __launch_bounds__(256) transpose_nk_kernel(const float* __restrict__ w, float* __restrict__ wt,
+                                                          int N, int K) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + threadIdx.x;
+    tile[r][threadIdx.x] = (n < N && k < K) ? w[(int64_t)n * K + k] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + threadIdx.x;
+    if (k < K && n < N) wt[(int64_t)k * N + n] = tile[threadIdx.x][r];
+  }
+}
+
 struct CudaBackend {
   cudaStream_t stream = nullptr;
   cudaError_t status = cudaSuccess;
+  // Pointwise forward / input-gradient products on the shared-memory tiled FP32 GEMM of the
+  // inference path (encoder.cu: pw_gemm_kernel) instead of the work-item functors that read
+  // both operands straight from global memory.  OAT_TRAIN_TILED=0 selects the functors.
+  static constexpr int kMaxWt = 1280 * 320;  // largest pointwise weight (features.18)
+  float* wt = nullptr;     // transposed-weight scratch
+  float* zeros = nullptr;  // zero bias
+  int tiled = -1;
+  CudaBackend() = default;
+  CudaBackend(const CudaBackend&) = delete;
+  CudaBackend& operator=(const CudaBackend&) = delete;
+  ~CudaBackend() {
+    if (wt) cudaFree(wt);
+    if (zeros) cudaFree(zeros);
+  }
+
+  bool tiled_ready() {
+    if (tiled < 0) {
+      const char* e = getenv("OAT_TRAIN_TILED");
+#ifndef OAT_TRAIN_TILED_DEFAULT
+#define OAT_TRAIN_TILED_DEFAULT 0
+#endif
+      tiled = e ? (atoi(e) != 0) : OAT_TRAIN_TILED_DEFAULT;
+      if (tiled) {
+        wt = static_cast<float*>(alloc((size_t)kMaxWt * sizeof(float)));
+        zeros = static_cast<float*>(alloc(1280 * sizeof(float)));
+        if (!wt || !zeros) tiled = 0;
+      }
+    }
+    return tiled == 1;
+  }
+  // R[m][n] = sum_k A[m][k] W[n][k]
+  bool pw_forward(const float* a, const float* w, float* r, int64_t M, int N, int K) {
+    if (!tiled_ready() || K % 8 != 0 || N % 4 != 0 || (int64_t)N * K > kMaxWt || N > 1280 ||
+        M > 0x7fffffff)
+      return false;
+    transpose_nk_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, stream>>>(w, wt, N, K);
+    g_launch_count++;
+    note(cudaGetLastError());
+    if (simt_pw_gemm(a, wt, zeros, nullptr, r, (int)M, K, N, 0, stream) != 0) note(cudaErrorUnknown);
+    return true;
+  }
+  // dA[m][k] (+)= sum_n G[m][n] W[n][k]: W [N][K] is already the [K'][N'] operand (K' = N, N' = K)
+  bool pw_backward_x(const float* g, const float* w, float* da, int64_t M, int N, int K, int accumulate) {
+    if (!tiled_ready() || N % 8 != 0 || K % 4 != 0 || K > 1280 || M > 0x7fffffff) return false;
+    if (simt_pw_gemm(g, w, zeros, accumulate ? da : nullptr, da, (int)M, N, K, 0, stream) != 0)
+      note(cudaErrorUnknown);
+    return true;
+  }
 
   void* alloc(size_t bytes) {
     void* p = nullptr;

@@ -282,8 +282,11 @@ struct TrainerT {
       const float* in = i == 0 ? visual : units[i - 1].A;
       if (u.type == kStem)
         run(M * 32, StemFwd{in, u.w.p, u.R, B, C, u.hin, u.hin, u.hout, u.hout});
-      else if (u.type == kPointwise)
-        run(chunks(M, 4) * (u.cout / 4), PwFwd{in, u.w.p, u.R, M, u.cout, u.cin});
+      else if (u.type == kPointwise) {
+        // a backend may supply a shared-memory tiled GEMM (CUDA); the functor is the fallback
+        if (!bk.pw_forward(in, u.w.p, u.R, M, u.cout, u.cin))
+          run(chunks(M, 4) * (u.cout / 4), PwFwd{in, u.w.p, u.R, M, u.cout, u.cin});
+      }
       else
         run(M * (u.cout / 4), DwFwd{in, u.w.p, u.R, B, u.hin, u.hin, u.hout, u.hout, u.cout, u.stride});
       batchnorm_forward(u, M);
@@ -343,7 +346,8 @@ struct TrainerT {
       if (u.type == kPointwise) {
         const int rows = pick_rows(M, (int64_t)(u.cout / 4) * (u.cin / 4), 8, 256);
         run(chunks(M, rows) * (u.cout / 4) * (u.cin / 4), PwBwdW{u.G, src.A, u.w.g, M, u.cout, u.cin, rows});
-        run(chunks(M, 4) * (u.cin / 4), PwBwdX{u.G, u.w.p, src.G, M, u.cout, u.cin, u.input_has_skip});
+        if (!bk.pw_backward_x(u.G, u.w.p, src.G, M, u.cout, u.cin, u.input_has_skip))
+          run(chunks(M, 4) * (u.cin / 4), PwBwdX{u.G, u.w.p, src.G, M, u.cout, u.cin, u.input_has_skip});
       } else {
         const int64_t Min = (int64_t)B * u.hin * u.hin;
         const int rows = pick_rows(M, c / 4, 16, 128);

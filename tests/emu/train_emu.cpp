@@ -21,6 +21,9 @@ struct HostBackend {
   void run(int64_t n, const F& f) {
     for (int64_t i = 0; i < n; ++i) f(i);
   }
+  // no tiled GEMM on the host: the work-item functors run
+  bool pw_forward(const float*, const float*, float*, int64_t, int, int) { return false; }
+  bool pw_backward_x(const float*, const float*, float*, int64_t, int, int, int) { return false; }
 };
 using Trainer = oat::train::TrainerT<HostBackend>;
 std::string g_err;
