@@ -4,8 +4,9 @@
 // sequence of launches).  This file supplies the CUDA backend — every functor becomes a
 // grid-stride kernel on the caller's stream — and the C-ABI entry points.
 //
-// First correct version: FP32 SIMT, register-tiled GEMMs straight from global memory,
-// reductions through atomics.  Accuracy matters more than speed here (the BatchNorm
+// FP32 SIMT: the pointwise forward and input-gradient products run on the shared-memory tiled
+// GEMM of the inference path (encoder.cu), the weight gradients and everything else as
+// register-tiled work items straight from global memory, reductions through atomics.  Accuracy matters more than speed here (the BatchNorm
 // backward over a handful of rows is badly conditioned — see DESIGN.md §9); the
 // tensor-core / fused-block treatment the inference path received comes next.
 #include <cmath>
@@ -76,7 +77,7 @@ struct CudaBackend {
     if (tiled < 0) {
       const char* e = getenv("OAT_TRAIN_TILED");
 #ifndef OAT_TRAIN_TILED_DEFAULT
-#define OAT_TRAIN_TILED_DEFAULT 0
+#define OAT_TRAIN_TILED_DEFAULT 1
 #endif
       tiled = e ? (atoi(e) != 0) : OAT_TRAIN_TILED_DEFAULT;
       if (tiled) {
