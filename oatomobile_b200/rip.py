@@ -121,7 +121,9 @@ class RIPScorer:
       graph = torch.cuda.CUDAGraph()
       before = N.launch_count()
       try:
-        with torch.cuda.graph(graph):
+        # thread_local: CUDA calls of other threads (e.g. the NCCL watchdog of a process
+        # group) must not invalidate this capture
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
           z = run()
       except Exception:  # capture not possible here (e.g. a foreign capture in progress):
         self._use_graphs = False  # keep working with one launch per kernel
