@@ -1,5 +1,6 @@
-// CUDA instantiation of the fused encoder-front bodies (fused_body.h): one CTA per
-// (model, image, row split), 256 threads, the wide intermediates in shared memory.
+// CUDA instantiation of the fused encoder-front bodies (fused_body.h): the executors
+// (`CudaExec` 256 threads, `SmallExec` 128 threads, `PipeExec` producer/consumer halves with
+// tcgen05 + TMEM + mbarriers), the kernels and their launchers.
 //
 // Replaces, for the first blocks of torchvision's MobileNetV2 as wrapped by
 // oatomobile/torch/networks/perception.py:25-55, the separate stem / depthwise / pointwise

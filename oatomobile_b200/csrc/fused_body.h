@@ -1,23 +1,28 @@
 // Fused front of the BEV encoder: CTA bodies that keep the wide intermediate tensors of
-// MobileNetV2's first blocks in shared memory instead of HBM.
+// MobileNetV2's first blocks (torchvision, as wrapped by perception.py:25-55) in shared memory
+// instead of HBM.  BatchNorms are folded at pack time (api.cu).
 //
-//   FrontBody      features.0 (3x3 s2 conv C->32 + BN + ReLU6) -> features.1 depthwise 3x3
-//                  (+BN+ReLU6) -> features.1 project 32->16 (+BN)       [perception.py:43-55]
-//   ExpandDwBody   expand 1x1 (cin -> 6 cin, +BN+ReLU6) -> depthwise 3x3 (stride 1|2,
-//                  +BN+ReLU6) of one inverted-residual block; the 6x expanded tensor lives
-//                  only as a ring of a few image rows in shared memory.  The project 1x1
-//                  stays on the tcgen05 GEMM (tc_gemm.cu).
+//   DwProjectBody     features.1: depthwise 3x3 (+BN+ReLU6) -> project 32->16 (+BN); one pair of
+//                     output rows per small CTA, the depthwise output only in shared memory.
+//   ExpandDwBody      expand 1x1 (cin -> 6 cin, +BN+ReLU6) -> depthwise 3x3 (stride 1|2,
+//                     +BN+ReLU6) of one inverted-residual block, FP32: walks the image top to
+//                     bottom; the 6x expanded tensor lives only as a ring of a few image rows.
+//   ExpandDwPipeBody  the same block with the expand GEMM on tcgen05 (3xTF32) and the CTA split
+//                     into a producer and a consumer half (see its header below).
+//   FrontBody         features.0 (3x3 s2 conv C->32 as im2col + GEMM) + features.1 in one
+//                     kernel (correct, not faster than separate launches; off by default).
+//   The project 1x1 of features.2-4 stays on the tcgen05 GEMM (tc_gemm.cu).
 //
-// Both walk an image top to bottom.  Per iteration: stage the next input rows (cp.async,
-// double-buffered, issued one iteration ahead), run the pointwise convolution of the new
-// rows as a register-tiled FP32 GEMM out of shared memory into the row ring, then slide the
-// 3x3 depthwise window over the ring.  BatchNorms are folded at pack time (api.cu).
+// Ring bodies, per iteration: stage the next input rows (cp.async, issued ahead), run the
+// pointwise convolution of the new rows into the row ring, slide the 3x3 depthwise window
+// over the ring.
 //
 // A body is written against an executor `X` that provides shared memory, `phase(f)` =
-// "run f(tid) for every thread, then barrier", and 16-byte asynchronous copies.  fused.cu
-// instantiates it with the CUDA executor (the product); tests/emu instantiates it with a
-// host loop so the `-m "not gpu"` suite can check the tiling, ring and padding logic
-// against the oracle without a GPU (test tooling, never loaded by the package).
+// "run f(tid) for every thread, then barrier", asynchronous copies and (pipelined body) the
+// tensor-core / hand-over primitives.  fused.cu instantiates it with the CUDA executors (the
+// product); tests/emu instantiates it with a host loop so the `-m "not gpu"` suite can check
+// the tiling, ring and padding logic against the oracle without a GPU (test tooling, never
+// loaded by the package).
 #pragma once
 
 #include <math.h>
