@@ -49,12 +49,16 @@ class Trainer:
     group: optional `torch.distributed` process group → data-parallel replicas; the
       gradients are summed over the group and scaled by 1/world inside the Adam kernel
       (the reference has no DDP).  BatchNorm statistics stay per replica.
+    use_cuda_graphs: EXPERIMENTAL (not yet validated on a B200; off by default) — replay the
+      ~640 launches of `forward_backward` as one CUDA graph per batch shape: the step's
+      inputs are copied into static buffers, the RNG draws (target noise, dropout mask) and
+      the Adam launch stay outside the graph.
   """
 
   def __init__(self, model, lr: float = 1e-3, weight_decay: float = 0.0,
                clip_gradients: bool = False, noise_level: float = 1e-2,
                betas=(0.9, 0.999), eps: float = 1e-8,
-               group: Optional["dist.ProcessGroup"] = None):
+               group: Optional["dist.ProcessGroup"] = None, use_cuda_graphs: bool = False):
     if isinstance(model, ImitativeModel):
       self._kind, self._keys = N.KIND_DIM, _DIM_KEYS
     elif isinstance(model, BehaviouralModel):
@@ -67,6 +71,8 @@ class Trainer:
     self.group = group
     self.world = dist.get_world_size(group) if group is not None else 1
     self.step_count = 0
+    self._use_graphs = bool(use_cuda_graphs)
+    self._graphs = {}  # (B, T, C, has_mask) -> (graph, static inputs, static outputs)
     params = list(model.parameters())
     if not params or not params[0].is_cuda:
       raise N.NativeLibraryError(
@@ -147,6 +153,18 @@ class Trainer:
       dropout_mask = torch.bernoulli(torch.full((B, 1280), keep, device=self.device)) / keep
     elif dropout_mask is not None:
       dropout_mask = N.require_cuda_f32(dropout_mask, "dropout_mask")
+    if self._use_graphs:
+      loss, z, pred = self._forward_backward_graphed(visual, scalars, target, dropout_mask)
+    else:
+      loss, z, pred = self._forward_backward_native(visual, scalars, target, dropout_mask)
+    with torch.no_grad():
+      for c in self._bn_counters:
+        c += 1
+    _bump_versions(self._bn_stats)  # running_mean / running_var were updated in place
+    return loss, (pred if pred is not None else z)
+
+  def _forward_backward_native(self, visual, scalars, target, dropout_mask):
+    B, T = target.shape[0], target.shape[1]
     loss = torch.empty(1, device=self.device)
     z = torch.empty(B, 64, device=self.device)
     pred = torch.empty(B, T, 2, device=self.device) if self._kind == N.KIND_CIL else None
@@ -154,11 +172,38 @@ class Trainer:
       N.check(N.lib().oat_train_forward_backward(
           self._ptr, visual.data_ptr(), scalars.data_ptr(), target.data_ptr(), N.ptr(dropout_mask),
           B, T, loss.data_ptr(), z.data_ptr(), N.ptr(pred), N.stream_ptr(self.device)))
+    return loss, z, pred
+
+  def _forward_backward_graphed(self, visual, scalars, target, dropout_mask):
+    """One CUDA-graph replay per step (EXPERIMENTAL).  The graph bakes in the static input /
+    output buffers and the trainer's activation workspace (which only grows with the batch
+    shape, hence the key).  Outputs are the graph's static tensors: valid until the next step."""
+    key = (tuple(visual.shape), tuple(scalars.shape), tuple(target.shape), dropout_mask is not None)
+    entry = self._graphs.get(key)
+    if entry is None:
+      static = [visual.clone(), scalars.clone(), target.clone(),
+                None if dropout_mask is None else dropout_mask.clone()]
+      # un-captured first: workspace reservation and lazy initialisation; gradients and the
+      # BatchNorm running statistics it changes are recomputed / restored below
+      stats = [b.clone() for b in self._bn_stats]
+      self._forward_backward_native(*static)
+      with torch.no_grad():
+        for b, s in zip(self._bn_stats, stats):
+          b.copy_(s)
+      torch.cuda.current_stream(self.device).synchronize()
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        out = self._forward_backward_native(*static)
+      entry = (graph, static, out)
+      self._graphs.clear()  # the workspace may have been reallocated for this shape
+      self._graphs[key] = entry
+    graph, static, out = entry
     with torch.no_grad():
-      for c in self._bn_counters:
-        c += 1
-    _bump_versions(self._bn_stats)  # running_mean / running_var were updated in place
-    return loss, (pred if pred is not None else z)
+      for dst, src in zip(static, (visual, scalars, target, dropout_mask)):
+        if dst is not None:
+          dst.copy_(src)
+    graph.replay()
+    return out
 
   def activation(self, index: int) -> torch.Tensor:
     """Post-activation output [rows, channels] of conv+BN unit `index` (0..51, NHWC rows) or
