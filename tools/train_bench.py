@@ -27,6 +27,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--batch", type=int, default=64)
   ap.add_argument("--no-cpu", action="store_true")
+  ap.add_argument("--graphs", action="store_true", help="Trainer(use_cuda_graphs=True) (experimental)")
   a = ap.parse_args()
   import oatomobile_b200 as ob
   from oatomobile_b200 import _native as N
@@ -42,7 +43,7 @@ def main():
     cls = ob.ImitativeModel if kind == "dim" else ob.BehaviouralModel
     model = cls(output_shape=(4, 2), in_channels=2)
     model.load_state_dict(sd)
-    trainer = Trainer(model.to(dev), lr=1e-3)
+    trainer = Trainer(model.to(dev), lr=1e-3, use_cuda_graphs=a.graphs)
     batch = dict(visual_features=visual.to(dev), velocity=scalars[:, 0:3].to(dev),
                  is_at_traffic_light=scalars[:, 3:4].to(dev), traffic_light_state=scalars[:, 4:5].to(dev),
                  player_future=torch.cat([target, torch.zeros(a.batch, 4, 1)], -1).to(dev))
