@@ -14,7 +14,7 @@ from typing import Any, Mapping, Optional, Sequence
 import numpy as np
 import torch
 
-from oatomobile_b200 import ops
+from oatomobile_b200 import geometry, ops
 from oatomobile_b200.models import BehaviouralModel, ImitativeModel
 
 
@@ -80,20 +80,22 @@ class SetPointAgent:
     self._steps_counter = 0
 
   def act(self, observation, *args, **kwargs):
-    """baselines/base.py:116-176 (replanning cadence, local->world, PID step)."""
-    from oatomobile.utils import carla as cutil  # CARLA-side helper of the reference
+    """baselines/base.py:116-176 (replanning cadence, local->world, PID step).  The plan's
+    frame change is `geometry.local2world` (utils/carla.py:677-700); only the waypoint lookup
+    and the PID step touch the CARLA PythonAPI."""
+    import carla  # pylint: disable=import-error  (the simulator's own API)
     loc, rot = observation["location"], observation["rotation"]
     if self._setpoints_buffer is None or self._steps_counter % self._replan_every_steps == 0:
       plan_ego = self(copy.deepcopy(observation), *args, **kwargs)
-      self._setpoints_buffer = cutil.local2world(current_location=loc, current_rotation=rot,
-                                                 local_locations=plan_ego)
+      self._setpoints_buffer = geometry.local2world(current_location=loc, current_rotation=rot,
+                                                    local_locations=plan_ego)
     else:
       self._setpoints_buffer = self._setpoints_buffer[1:]
     self._steps_counter += 1
     speed = np.linalg.norm(np.diff(self._setpoints_buffer[:self._setpoint_index], axis=0),
                            axis=1).mean() / self._fixed_delta_seconds_between_setpoints
     setpoint = self._map.get_waypoint(
-        cutil.ndarray_to_location(self._setpoints_buffer[self._setpoint_index]))
+        carla.Location(*map(float, self._setpoints_buffer[self._setpoint_index])))
     if self._steps_counter <= 100:
       speed = 20.0 / 3.6
     return self._vehicle_controller.run_step(target_speed=speed * 3.6, waypoint=setpoint)

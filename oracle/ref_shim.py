@@ -1,9 +1,9 @@
 """TEST INFRASTRUCTURE ONLY — import shim for the *real* reference (OATML/oatomobile).
 
 Only usable where ``/root/reference`` exists (the build container, NOT the GPU
-box).  It is used by ``tests/golden/make_golden.py`` to generate the committed
-golden vectors and by ``tests/test_oracle_vs_reference.py`` to pin the in-repo
-restatement (``oracle/restatement.py``) against the reference itself.
+box).  It is used by ``tests/golden/make_golden*.py`` to generate the committed
+golden vectors; ``tests/test_oracle_golden.py`` then pins the in-repo restatement
+(``oracle/restatement.py``) against those vectors on every CPU run.
 
 Nothing on the product path may import this module.
 
@@ -96,6 +96,36 @@ def install():
 
   torch.hub.load = _hub_load
   _installed = True
+
+
+def install_carla_stubs():
+  """For the reference's geometry helpers (oatomobile/utils/carla.py:642-700): a `carla`
+  stub whose `Rotation(pitch, yaw, roll)` / `Location(x, y, z)` keep their arguments, and
+  `transforms3d.euler.euler2mat` served by the restatement in oracle/euler.py (transforms3d
+  0.3.1 is neither vendored in the reference nor installed here)."""
+  install()
+  from oracle import euler as _euler
+
+  class _Rotation:
+
+    def __init__(self, pitch=0.0, yaw=0.0, roll=0.0):
+      self.pitch, self.yaw, self.roll = pitch, yaw, roll
+
+  class _Location:
+
+    def __init__(self, x=0.0, y=0.0, z=0.0):
+      self.x, self.y, self.z = x, y, z
+
+  carla = sys.modules["carla"]
+  carla.Rotation, carla.Location = _Rotation, _Location
+  t3d = sys.modules["transforms3d"]
+  t3d.euler = types.ModuleType("transforms3d.euler")
+  t3d.euler.euler2mat = _euler.euler2mat
+  sys.modules["transforms3d.euler"] = t3d.euler
+  import importlib
+  cutil = importlib.import_module("oatomobile.utils.carla")
+  cutil.carla, cutil.transforms3d = carla, t3d
+  return cutil
 
 
 def fix_locscale(model):

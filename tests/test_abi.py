@@ -51,6 +51,9 @@ def test_product_never_imports_the_oracle():
         bad = re.search(r"(from|import)\s+oracle|oracle[./](restatement|ref_shim|_ref)|"
                         r"#include\s*[\"<].*oracle", text)
         assert bad is None, (os.path.join(dirpath, f), bad.group(0))
+        if f.endswith(".py"):  # nor the reference package itself (agents.py did)
+          ref = re.search(r"^\s*(from\s+oatomobile(\.|\s)|import\s+oatomobile(\.|\s|$))", text, re.M)
+          assert ref is None, (os.path.join(dirpath, f), ref.group(0))
 
 
 def test_error_behaviour_matches_reference():
