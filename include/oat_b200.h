@@ -47,7 +47,8 @@ typedef struct OatTensor {
 typedef struct OatModel OatModel;       /* one ImitativeModel / BehaviouralModel */
 typedef struct OatEnsemble OatEnsemble; /* E models on one GPU + workspace       */
 
-enum { OAT_KIND_DIM = 0, OAT_KIND_CIL = 1, OAT_KIND_FLOW = 2 /* AutoregressiveFlow alone */ };
+enum { OAT_KIND_DIM = 0, OAT_KIND_CIL = 1, OAT_KIND_FLOW = 2 /* AutoregressiveFlow alone */,
+       OAT_KIND_ENCODER = 3 /* MobileNetV2 alone: keys `_model.features...`, `_model.classifier.1` */ };
 enum { OAT_ALGO_WCM = 0, OAT_ALGO_BCM = 1, OAT_ALGO_MA = 2 };
 
 OAT_API const char* oat_last_error(void);
@@ -105,6 +106,22 @@ OAT_API int oat_transform_visual(const float* lidar, int32_t B, int32_t C, int32
  * the HWC->CHW transposes of rip/agent.py:69 and datasets/carla.py:138-140.           */
 OAT_API int oat_transform_visual_hwc(const float* lidar, int32_t B, int32_t H, int32_t W, int32_t C,
                              float* visual, void* stream);
+
+/* `MobileNetV2.forward` (oatomobile/torch/networks/perception.py:53-55) for every model of
+ * the ensemble, eval mode: visual [B,C,100,100] -> features [E,B,128] (stem, 17 inverted-
+ * residual blocks, 1x1 320->1280, global average pool, Linear 1280->128; no merger).  Works
+ * for ensembles of any kind, including OAT_KIND_ENCODER (a MobileNetV2 module on its own). */
+OAT_API int oat_encode_features(OatEnsemble* ens, const float* visual, int32_t B, float* features,
+                        void* stream);
+
+/* `MLP.forward` (oatomobile/torch/networks/mlp.py:70-72) for a ReLU stack: layer l is
+ * Linear(sizes[l] -> sizes[l+1]) with DEVICE pointers weights[l] = W [sizes[l+1]][sizes[l]]
+ * (PyTorch layout) and biases[l] (or null); ReLU after every layer but the last, and after
+ * the last iff `activate_final` (mlp.py:65-66).  x [B,sizes[0]] -> out [B,sizes[num_layers]].
+ * One launch; 1 <= num_layers <= 8, widths <= 4096.  The pointer arrays live on the host. */
+OAT_API int oat_mlp_forward(const float* const* weights, const float* const* biases,
+                    const int32_t* sizes, int32_t num_layers, int32_t activate_final,
+                    const float* x, int32_t B, float* out, void* stream);
 
 /* `ImitativeModel._params` (dim/model.py:173-219) for every model of the ensemble:
  * visual [B,C,100,100] (shared), scalars [B,S] = cat(velocity(3), is_at_traffic_light(1),
@@ -249,6 +266,15 @@ OAT_API int oat_adam_step(float* param, const float* grad, float* exp_avg, float
 /* Number of kernel launches issued by this library since load (bench.py's
  * `gpu_launches`). */
 OAT_API int64_t oat_launch_count(void);
+
+/* Per-kernel-family device timing for bench.py's `roofline` (no reference counterpart: the
+ * reference has no profiler hook).  Between begin and end every kernel this
+ * library launches is followed by a cudaEventRecord on its stream; `oat_profile_end`
+ * synchronises, attributes the time between consecutive events to the launch in between and
+ * writes {"<family>": {"ms": total, "launches": n}, ...} as NUL-terminated JSON text.
+ * Launch the kernels one by one while a profile is open (not inside a stream capture).   */
+OAT_API int oat_profile_begin(void* stream);
+OAT_API int oat_profile_end(char* json, int64_t capacity);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OAT_B200_LIB", os.path.join(_HERE, "liboat_b200.so"))
 
-KIND_DIM, KIND_CIL, KIND_FLOW = 0, 1, 2
+KIND_DIM, KIND_CIL, KIND_FLOW, KIND_ENCODER = 0, 1, 2, 3
 ALGORITHMS = {"WCM": 0, "BCM": 1, "MA": 2}
 
 # Every symbol include/oat_b200.h declares (checked by tests/test_abi.py).
@@ -27,7 +27,8 @@ SYMBOLS = (
     "oat_transform_visual_hwc", "oat_lidar_bev", "oat_trainer_create", "oat_trainer_destroy",
     "oat_train_forward_backward", "oat_adam_step", "oat_trainer_activation",
     "oat_ensemble_set_fusion", "oat_ensemble_get_fusion", "oat_debug_encoder_prefix",
-    "oat_ensemble_set_fusion_tc",
+    "oat_ensemble_set_fusion_tc", "oat_profile_begin", "oat_profile_end",
+    "oat_encode_features", "oat_mlp_forward",
 )
 
 
@@ -90,6 +91,11 @@ def lib() -> ctypes.CDLL:
     L.oat_ensemble_set_fusion_tc.argtypes = [vp, c_i32]
     L.oat_debug_encoder_prefix.argtypes = [vp, vp, c_i32, c_i32, vp, vp]
     L.oat_set_flow_impl.argtypes = [c_i32]
+    L.oat_encode_features.argtypes = [vp, vp, c_i32, vp, vp]
+    L.oat_mlp_forward.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(c_i32), c_i32,
+                                  c_i32, vp, c_i32, vp, vp]
+    L.oat_profile_begin.argtypes = [vp]
+    L.oat_profile_end.argtypes = [ctypes.c_char_p, c_i64]
     L.oat_plan.argtypes = [ctypes.POINTER(vp), c_i32, c_i32, vp, vp, c_i32, c_f, c_i32, c_i32, c_i32,
                            c_f, vp, vp, vp, vp, c_i64, vp, vp]
     L.oat_plan_workspace_floats.argtypes = [c_i32, c_i32, c_i32]
@@ -212,6 +218,8 @@ class ModelHandle:
 class EnsembleHandle:
   """Owns one `OatEnsemble*` over E model handles living on the same GPU."""
 
+  _generation = 0
+
   def __init__(self, models: Sequence[ModelHandle]):
     L = lib()
     self.models = list(models)  # keep the model handles alive
@@ -220,6 +228,10 @@ class EnsembleHandle:
     check(L.oat_ensemble_create(arr, len(models), ctypes.byref(out)))
     self.ptr = out
     self.device = models[0].device
+    self.in_channels = int(L.oat_model_in_channels(models[0].ptr))
+    self.scalars = {KIND_CIL: 6, KIND_ENCODER: 0}.get(models[0].kind, 5)  # merger inputs besides the 128 features
+    EnsembleHandle._generation += 1
+    self.generation = EnsembleHandle._generation  # never reused (unlike id()): keys CUDA graphs
     if _default_pw_impl != "tcgen05":
       self.set_pw_impl(_default_pw_impl)
     if _default_fusion is not None:
@@ -254,3 +266,17 @@ class EnsembleHandle:
         self.ptr = None
     except Exception:
       pass
+
+
+def profile_begin(device) -> None:
+  """Opens a per-kernel-family device timing (include/oat_b200.h: oat_profile_begin)."""
+  with torch.cuda.device(device):
+    check(lib().oat_profile_begin(stream_ptr(device)))
+
+
+def profile_end() -> dict:
+  """Closes it: {"family": {"ms": total, "launches": n}, ...}."""
+  import json
+  buf = ctypes.create_string_buffer(1 << 16)
+  check(lib().oat_profile_end(buf, len(buf)))
+  return json.loads(buf.value.decode())

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liboat_b200.so")
-SOURCES = ["api.cu", "flow.cu", "aggregate.cu", "encoder.cu", "tc_gemm.cu", "flow_tc.cu", "flow_tc2.cu", "planner.cu", "lidar.cu", "train.cu", "fused.cu"]
+SOURCES = ["api.cu", "flow.cu", "aggregate.cu", "encoder.cu", "tc_gemm.cu", "flow_tc.cu", "flow_tc2.cu", "planner.cu", "lidar.cu", "train.cu", "fused.cu", "mlp.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -109,7 +109,7 @@ int launch_goal_likelihood(const float* y_last, const float* goal, int B, int G,
   goal_likelihood_kernel<<<1, 256, 0, stream>>>(
       y_last, goal, B, G, (float)(1.0 / (2.0 * eps * eps)),
       (float)(-log(2.0 * 3.14159265358979323846 * eps * eps) - log((double)G)), rows, mean);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED("goal_likelihood");
   return 0;
 }
 
@@ -120,7 +120,7 @@ int launch_aggregate(const float* q, int E, int B, int K, int algo, const float*
   if (E < 1 || K < 1) return fail("aggregate: need E >= 1 and K >= 1");
   if (algo < OAT_ALGO_WCM || algo > OAT_ALGO_MA) return fail("aggregate: unknown algorithm");
   aggregate_kernel<<<B, ATHREADS, 0, stream>>>(q, E, B, K, algo, y, T, s, kstar, sbest, plan);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED("aggregate");
   return 0;
 }
 

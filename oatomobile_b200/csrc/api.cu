@@ -6,6 +6,7 @@
 // precision), transposes every matrix into the K-major layout the kernels read
 // and uploads one arena per model.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -22,6 +23,23 @@ int64_t g_launch_count = 0;
 #define OAT_FLOW_DEFAULT_IMPL 2
 #endif
 int g_flow_impl = OAT_FLOW_DEFAULT_IMPL;
+
+bool g_profile_on = false;
+namespace {
+struct ProfileMark {
+  const char* tag;
+  cudaEvent_t ev;
+};
+std::vector<ProfileMark> g_profile_marks;
+std::mutex g_profile_mutex;
+}  // namespace
+void profile_mark(const char* tag, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, stream);
+  g_profile_marks.push_back({tag, ev});
+}
 
 void set_error(const std::string& msg) { g_error = msg; }
 int fail(const std::string& msg) {
@@ -138,10 +156,63 @@ const char* oat_last_error(void) { return g_error.c_str(); }
 int oat_abi_version(void) { return OAT_ABI_VERSION; }
 int64_t oat_launch_count(void) { return g_launch_count; }
 
+int oat_profile_begin(void* stream) {
+  if (g_profile_on) return fail("oat_profile_begin: a profile is already open");
+  {
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    g_profile_marks.clear();
+  }
+  g_profile_on = true;
+  profile_mark("", (cudaStream_t)stream);  // origin of the first interval
+  return 0;
+}
+
+int oat_profile_end(char* json, int64_t capacity) {
+  if (!g_profile_on) return fail("oat_profile_end: no profile is open");
+  g_profile_on = false;
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
+  std::map<std::string, std::pair<double, int64_t>> acc;  // tag -> (ms, launches)
+  cudaError_t err = cudaSuccess;
+  if (!g_profile_marks.empty()) err = cudaEventSynchronize(g_profile_marks.back().ev);
+  for (size_t i = 1; i < g_profile_marks.size() && err == cudaSuccess; ++i) {
+    float ms = 0.f;
+    err = cudaEventElapsedTime(&ms, g_profile_marks[i - 1].ev, g_profile_marks[i].ev);
+    auto& a = acc[g_profile_marks[i].tag];
+    a.first += ms;
+    a.second += 1;
+  }
+  for (auto& m : g_profile_marks) cudaEventDestroy(m.ev);
+  g_profile_marks.clear();
+  if (err != cudaSuccess) return fail(std::string("oat_profile_end: ") + cudaGetErrorString(err));
+  std::string out = "{";
+  for (auto it = acc.begin(); it != acc.end(); ++it) {
+    if (it != acc.begin()) out += ", ";
+    char buf[512];
+    std::string tag = it->first;  // training functors: keep the type name of "[with F = ...]"
+    const size_t w = tag.find("F = ");
+    if (w != std::string::npos) {
+      tag = tag.substr(w + 4);
+      const size_t e = tag.find_first_of(";]");
+      if (e != std::string::npos) tag = tag.substr(0, e);
+      const size_t c = tag.rfind("::");
+      if (c != std::string::npos) tag = tag.substr(c + 2);
+    }
+    for (auto& ch : tag) if (ch == '"' || ch == '\\') ch = '_';
+    if (tag.size() > 200) tag.resize(200);
+    snprintf(buf, sizeof(buf), "\"%s\": {\"ms\": %.6f, \"launches\": %lld}", tag.c_str(),
+             it->second.first, (long long)it->second.second);
+    out += buf;
+  }
+  out += "}";
+  if (!json || capacity < (int64_t)out.size() + 1) return fail("oat_profile_end: buffer too small");
+  memcpy(json, out.c_str(), out.size() + 1);
+  return 0;
+}
+
 int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind, int32_t device,
                      OatModel** out) {
   if (!tensors || !out) return fail("oat_model_create: null argument");
-  if (kind != OAT_KIND_DIM && kind != OAT_KIND_CIL && kind != OAT_KIND_FLOW)
+  if (kind != OAT_KIND_DIM && kind != OAT_KIND_CIL && kind != OAT_KIND_FLOW && kind != OAT_KIND_ENCODER)
     return fail("oat_model_create: bad kind");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -157,7 +228,9 @@ int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind
     for (int d = 0; d < t.ndim && d < 4; ++d) h.shape.push_back(t.shape[d]);
     P.sd[t.name] = h;
   }
-  const std::string enc = "_encoder._model.";
+  // a stand-alone `MobileNetV2` module (perception.py:25-55) carries its keys without the
+  // `_encoder.` prefix and has neither merger nor decoder
+  const std::string enc = kind == OAT_KIND_ENCODER ? "_model." : "_encoder._model.";
   const std::string f = enc + "features.";
 
   // ---- stem: features.0 = conv3x3 s2 (C->32) + BN + ReLU6 (perception.py:43-51)
@@ -224,13 +297,15 @@ int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind
   if (has_encoder) {
     if (!pack_pw(P, f + "18.0", f + "18.1", 320, 1280, &last)) return fail(P.err);
     if (!pack_linear(P, enc + "classifier.1", 1280, OAT_ENC_FEATURES, &fc)) return fail(P.err);
-    if (!pack_linear(P, "_merger._model.0", OAT_ENC_FEATURES + S, 64, &mg[0])) return fail(P.err);
-    if (!pack_linear(P, "_merger._model.2", 64, 64, &mg[1])) return fail(P.err);
-    if (!pack_linear(P, "_merger._model.4", 64, 64, &mg[2])) return fail(P.err);
+    if (kind != OAT_KIND_ENCODER) {
+      if (!pack_linear(P, "_merger._model.0", OAT_ENC_FEATURES + S, 64, &mg[0])) return fail(P.err);
+      if (!pack_linear(P, "_merger._model.2", 64, 64, &mg[1])) return fail(P.err);
+      if (!pack_linear(P, "_merger._model.4", 64, 64, &mg[2])) return fail(P.err);
+    }
   }
 
   // ---- GRU + head (sequence.py:53-65) / CIL GRU + output (cil/model.py:60-66)
-  {
+  if (kind != OAT_KIND_ENCODER) {
     const std::string g = (kind == OAT_KIND_DIM) ? "_decoder._decoder." : "_decoder.";  // FLOW == CIL key
     const HostTensor *wih = P.get(g + "weight_ih", {192, 2}), *whh = P.get(g + "weight_hh", {192, 64}),
                      *bih = P.get(g + "bias_ih", {192}), *bhh = P.get(g + "bias_hh", {192});
@@ -270,7 +345,7 @@ int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind
   }
 
   Off flow_tc{0, 0};
-  if (kind != OAT_KIND_CIL) {
+  if (kind != OAT_KIND_CIL && kind != OAT_KIND_ENCODER) {
     flow_tc.w = P.alloc(kFlowTcFloats);
     pack_flow_tc_image(P.arena.data() + flow.w, P.arena.data() + flow_tc.w);
   }
@@ -313,8 +388,8 @@ int oat_model_create(const OatTensor* tensors, int32_t num_tensors, int32_t kind
   m->last = dev(last);
   m->fc = dev(fc);
   for (int i = 0; i < 3; ++i) m->merger[i] = dev(mg[i]);
-  m->flow = m->arena + flow.w;
-  m->flow_tc = (kind != OAT_KIND_CIL) ? m->arena + flow_tc.w : nullptr;
+  m->flow = kind != OAT_KIND_ENCODER ? m->arena + flow.w : nullptr;
+  m->flow_tc = (kind != OAT_KIND_CIL && kind != OAT_KIND_ENCODER) ? m->arena + flow_tc.w : nullptr;
   *out = m;
   return 0;
 }
@@ -527,6 +602,24 @@ int oat_encode(OatEnsemble* ens, const float* visual, const float* scalars, int3
   if (int rc = check_device(ens->device, "oat_encode")) return rc;
   if (int rc = oat_ensemble_reserve(ens, B)) return rc;
   return encoder_forward(ens, visual, scalars, B, z, (cudaStream_t)stream);
+}
+
+int oat_encode_features(OatEnsemble* ens, const float* visual, int32_t B, float* features,
+                        void* stream) {
+  if (B <= 0) return 0;
+  if (!ens || !visual || !features) return fail("oat_encode_features: null argument");
+  if (int rc = check_device(ens->device, "oat_encode_features")) return rc;
+  if (int rc = oat_ensemble_reserve(ens, B)) return rc;
+  // stop_after_blocks = 18: the whole MobileNetV2 (features + pool + classifier), no merger
+  return encoder_forward(ens, visual, nullptr, B, nullptr, (cudaStream_t)stream, 18, features);
+}
+
+int oat_mlp_forward(const float* const* weights, const float* const* biases, const int32_t* sizes,
+                    int32_t num_layers, int32_t activate_final, const float* x, int32_t B, float* out,
+                    void* stream) {
+  if (B <= 0) return 0;
+  if (!weights || !sizes || !x || !out) return fail("oat_mlp_forward: null argument");
+  return launch_mlp(weights, biases, sizes, num_layers, activate_final, x, B, out, (cudaStream_t)stream);
 }
 
 int oat_debug_encoder_prefix(OatEnsemble* ens, const float* visual, int32_t B, int32_t blocks,

@@ -34,6 +34,17 @@ extern int64_t g_launch_count;
       return ::oat::fail(std::string("kernel launch: ") + cudaGetErrorString(_e)); \
   } while (0)
 
+// Per-kernel-family timing for bench.py's roofline (api.cu: oat_profile_begin/_end): while a
+// profile is open every tagged launch is followed by a cudaEventRecord on its stream; the
+// time between consecutive events is attributed to the launch in between.  No-op otherwise.
+extern bool g_profile_on;
+void profile_mark(const char* tag, cudaStream_t stream);
+#define OAT_LAUNCHED(tag)                                                       \
+  do {                                                                          \
+    OAT_LAUNCH_CHECK();                                                         \
+    if (::oat::g_profile_on) ::oat::profile_mark(tag, stream);                  \
+  } while (0)
+
 // ---- packed flow (GRU + head) weights, one contiguous device buffer per model
 // Layout (floats), identical to the shared-memory image the flow kernel uses:
 //   whhT [64][192]  W_hh transposed (k-major; columns = gate r|z|n x unit)
@@ -177,6 +188,8 @@ int launch_aggregate(const float* q, int E, int B, int K, int algo, const float*
                      float* s, int32_t* kstar, float* sbest, float* plan,
                      cudaStream_t stream);
 
+int launch_mlp(const float* const* w, const float* const* b, const int* sizes, int layers,
+               int activate_final, const float* x, int B, float* out, cudaStream_t stream);
 int simt_pw_gemm(const float* A, const float* W_kn, const float* bias, const float* R, float* C,
                  int M, int K, int N, int relu6, cudaStream_t stream);
 int launch_transform_visual(const float* lidar, int B, int C, int H, int W, float* visual,

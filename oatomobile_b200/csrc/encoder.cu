@@ -341,7 +341,7 @@ int launch_pw(const PwArgs& a, int E, cudaStream_t stream, const TcLayer* tc = n
     dim3 grid((a.M + 127) / 128, (a.N + 63) / 64, E);
     pw_gemm_kernel<128, 64, 8, 4><<<grid, 256, 0, stream>>>(a);
   }
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED("simt_pw_gemm");
   return 0;
 }
 
@@ -576,7 +576,7 @@ int launch_transform_visual(const float* lidar, int B, int C, int H, int W, floa
   else
     transform_visual_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
         lidar, B * C, C, H, W, visual, sh, sw);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED("transform");
   return 0;
 }
 
@@ -620,7 +620,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
     dim3 grid((unsigned)(((int64_t)B * 2500 + STEM_THREADS - 1) / STEM_THREADS), E);
 #endif
     stem_kernel<<<grid, STEM_THREADS, 0, stream>>>(w, b, visual, B, C, ens->bufA);
-    OAT_LAUNCH_CHECK();
+    OAT_LAUNCHED("stem");
   }
   auto prefix_done = [&](size_t blocks_done, const float* act, int h, int c) -> int {
     if (stop_after_blocks < 0 || (size_t)stop_after_blocks != blocks_done) return 0;
@@ -697,7 +697,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       else
 #endif
         dw_kernel<2><<<grid, OAT_DW_THREADS, 0, stream>>>(w, b, dw_in, ens->bufH2, B, blk.hin, blk.hout, blk.hid);
-      OAT_LAUNCH_CHECK();
+      OAT_LAUNCHED("depthwise");
     }
     {  // project 1x1 + BN (linear) + residual
       PwArgs a;
@@ -726,7 +726,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
     const int64_t rows = (int64_t)E * B;
     pool_kernel<<<(unsigned)((rows * 1280 + 255) / 256), 256, 0, stream>>>(ens->bufH1, ens->pooled,
                                                                           rows, P, 1280);
-    OAT_LAUNCH_CHECK();
+    OAT_LAUNCHED("pool");
   }
   {  // classifier.1: Linear 1280 -> 128 (Dropout is identity in eval)
     PwArgs a;
@@ -737,6 +737,12 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
     a.M = B; a.K = 1280; a.N = 128; a.relu6 = 0;
     if (int rc = launch_pw(a, E, stream, tc())) return rc;
   }
+  if (stop_after_blocks == 18) {  // `MobileNetV2.forward` alone: the 128 features, no merger
+    OAT_CUDA(cudaMemcpyAsync(prefix_out, ens->feat, (size_t)E * B * 128 * sizeof(float),
+                             cudaMemcpyDeviceToDevice, stream));
+    return 0;
+  }
+  if (m0->kind == OAT_KIND_ENCODER) return fail("encoder: a MobileNetV2-only model has no merger");
   {  // merger MLP -> z [E][B][64]
     MergerArgs a;
     a.w0 = table([](const OatModel* m) { return m->merger[0].w; });
@@ -747,7 +753,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
     a.b2 = table([](const OatModel* m) { return m->merger[2].b; });
     a.feat = ens->feat; a.scalars = scalars; a.B = B; a.S = m0->scalars; a.z = z;
     merger_kernel<<<dim3(B, E), 64, 0, stream>>>(a);
-    OAT_LAUNCH_CHECK();
+    OAT_LAUNCHED("merger");
   }
   return 0;
 }

@@ -352,7 +352,7 @@ int launch_mode(const FlowArgs& fa, int num_models, cudaStream_t stream) {
   }
   dim3 grid((unsigned)((fa.N + FR - 1) / FR), (unsigned)num_models);
   flow_kernel<MODE><<<grid, FTHREADS, smem, stream>>>(fa);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED(MODE == 0 ? "flow_sample" : MODE == 1 ? "flow_score" : "cil_rollout");
   return 0;
 }
 

@@ -442,7 +442,7 @@ int launch_tc_mode(const FlowTcArgs& fa, int num_models, cudaStream_t stream) {
   }
   dim3 grid((unsigned)((fa.N + TR - 1) / TR), (unsigned)num_models);
   flow_tc_kernel<MODE><<<grid, TTHREADS, smem, stream>>>(fa);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED(MODE == 0 ? "flow_sample" : "flow_score");
   return 0;
 }
 

@@ -484,7 +484,7 @@ int launch_tc2_mode(const FlowTc2Args& fa, int num_models, cudaStream_t stream) 
   }
   dim3 grid((unsigned)((fa.N + 2 * TR - 1) / (2 * TR)), (unsigned)num_models);
   flow_tc2_kernel<MODE><<<grid, TTHREADS, smem, stream>>>(fa);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED(MODE == 0 ? "flow_sample" : "flow_score");
   return 0;
 }
 

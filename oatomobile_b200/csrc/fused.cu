@@ -342,7 +342,7 @@ int launch_tc_body(const FusedBlockLaunch& l, cudaStream_t stream) {
   // persistent: one CTA per SM walks the units with a stride (weights reloaded per model only)
   const int grid = a.units < sms ? a.units : sms;
   expand_dw_tc_kernel<Body><<<grid, kPipeThreads, smem, stream>>>(a);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED("fused_expand_dw");
   return 0;
 }
 
@@ -358,7 +358,7 @@ int launch_body(const FusedBlockLaunch& l, cudaStream_t stream) {
   if (int rc = allow_smem(expand_dw_kernel<Body>, smem, configured)) return rc;
   const int64_t ctas = (int64_t)l.E * l.B * a.splits;
   expand_dw_kernel<Body><<<(unsigned)ctas, kFusedThreads, smem, stream>>>(a);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED("fused_expand_dw");
   return 0;
 }
 
@@ -402,7 +402,7 @@ int launch_fused_dw_project(const FusedDwProjectLaunch& l, cudaStream_t stream) 
   const int64_t ctas = (int64_t)l.E * l.B * fused::DwProjectBody::PAIRS;
   if (ctas > 0x7fffffff) return fail("fused encoder kernel: batch too large");
   dw_project_kernel<<<(unsigned)ctas, kDwProjectThreads, 0, stream>>>(a);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED("fused_dw_project");
   return 0;
 }
 
@@ -419,7 +419,7 @@ int launch_fused_front(const FusedFrontLaunch& l, cudaStream_t stream) {
   if (int rc = allow_smem(front_kernel, smem, configured)) return rc;
   const int64_t ctas = (int64_t)l.E * l.B * a.splits;
   front_kernel<<<(unsigned)ctas, kFusedThreads, smem, stream>>>(a);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED("fused_front");
   return 0;
 }
 

@@ -585,7 +585,7 @@ int tc_pw_gemm(const TcGemmProblem& p, cudaStream_t stream) {
   const int tiles = a.m_tiles * a.n_tiles * a.E;
   const int grid = tiles < sms ? tiles : sms;
   tc_pw_gemm_kernel<<<grid, TC_THREADS, smem, stream>>>(a);
-  OAT_LAUNCH_CHECK();
+  OAT_LAUNCHED("tc_pw_gemm");
   return 0;
 }
 

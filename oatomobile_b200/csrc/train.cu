@@ -95,6 +95,7 @@ struct CudaBackend {
       return false;
     transpose_nk_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, stream>>>(w, wt, N, K);
     g_launch_count++;
+    if (g_profile_on) profile_mark("train_transpose", stream);
     note(cudaGetLastError());
     if (simt_pw_gemm(a, wt, zeros, nullptr, r, (int)M, K, N, 0, stream) != 0) note(cudaErrorUnknown);
     return true;
@@ -125,6 +126,8 @@ struct CudaBackend {
     if (e != cudaSuccess && status == cudaSuccess) status = e;
   }
   template <class F>
+  static const char* functor_tag() { return __PRETTY_FUNCTION__; }  // "... [with F = oat::train::X]"
+  template <class F>
   void run(int64_t n, const F& f) {
     if (n <= 0) return;
     constexpr int kBlock = BlockSize<F>::value;
@@ -133,6 +136,7 @@ struct CudaBackend {
     if (blocks > cap) blocks = cap;
     run_functor<F><<<(unsigned)blocks, kBlock, 0, stream>>>(f, n);
     g_launch_count++;
+    if (g_profile_on) profile_mark(functor_tag<F>(), stream);
     note(cudaGetLastError());
   }
 };

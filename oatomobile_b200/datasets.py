@@ -75,40 +75,51 @@ class CARLADataset:
 
 
 class DeviceCollator:
-  """B200-side batching: stacks HWC `lidar` straight from the `.npz` payload into one
-  pinned buffer, ships it with a single async H2D copy and lets one CUDA kernel do
-  cast-free HWC→CHW + bilinear 200→100 + H↔W (`oat_transform_visual_hwc`), i.e. the
-  per-sample `np.transpose` and the model's `transform` never run on the host."""
+  """B200-side batching for `DataLoader(collate_fn=...)`: stacks the samples of a batch into
+  pinned host buffers and ships every key with one asynchronous H2D copy each.
+
+  The grid is emitted RAW under `lidar`, in the layout the samples carry ([B,200,200,C] HWC as
+  stored in the `.npz`, or CHW from `as_torch`), so the documented loop
+  `batch = model.transform(batch)` (dim/train.py:176-178) does the rest exactly once:
+  `transform` renames it to `visual_features`, runs the fused HWC->CHW + bilinear 200->100 +
+  H<->W kernel (`oat_transform_visual_hwc`; the per-sample `np.transpose` never runs on the
+  host), keeps `num_timesteps_to_keep` targets and (CIL) remaps the STOP mode.
+
+  Pinned staging is double-buffered: the H2D copies are asynchronous, so a slot is only
+  rewritten after the CUDA event recorded behind its previous copies has completed."""
+
+  _SLOTS = 2
 
   def __init__(self, device, keys=("velocity", "is_at_traffic_light", "traffic_light_state",
                                    "player_future", "mode")):
     self._device = torch.device(device)
     self._keys = keys
-    self._pinned = {}
+    self._pinned = [dict() for _ in range(self._SLOTS)]
+    self._copied = [None] * self._SLOTS   # event recorded after the slot's last H2D copies
+    self._slot = 0
 
-  def _pin(self, name, shape):
-    buf = self._pinned.get(name)
+  def _pin(self, slot, name, shape):
+    buf = self._pinned[slot].get(name)
     if buf is None or tuple(buf.shape) != tuple(shape):
       buf = torch.empty(shape, dtype=torch.float32, pin_memory=True)
-      self._pinned[name] = buf
+      self._pinned[slot][name] = buf
     return buf
 
   def __call__(self, samples: Sequence[Mapping[str, np.ndarray]]) -> Mapping[str, torch.Tensor]:
-    from oatomobile_b200 import ops
+    slot = self._slot
+    self._slot = (slot + 1) % self._SLOTS
+    if self._copied[slot] is not None:
+      self._copied[slot].synchronize()  # the DMA that last read this slot has finished
     out = {}
-    lidar = samples[0].get("lidar")
-    if lidar is not None:
-      hwc = lidar.ndim == 3 and lidar.shape[-1] <= 8
-      buf = self._pin("lidar", (len(samples),) + tuple(lidar.shape))
+    for k in ("lidar",) + tuple(self._keys):
+      if k not in samples[0]:
+        continue
+      v0 = np.atleast_1d(samples[0][k])
+      buf = self._pin(slot, k, (len(samples),) + tuple(v0.shape))
       for i, s in enumerate(samples):
-        buf[i].copy_(torch.from_numpy(np.ascontiguousarray(s["lidar"], dtype=np.float32)))
-      dev = buf.to(self._device, non_blocking=True)
-      out["visual_features"] = ops.transform_visual_hwc(dev) if hwc else ops.transform_visual(dev)
-    for k in self._keys:
-      if k in samples[0]:
-        v0 = np.atleast_1d(samples[0][k])
-        buf = self._pin(k, (len(samples),) + tuple(v0.shape))
-        for i, s in enumerate(samples):
-          buf[i].copy_(torch.from_numpy(np.atleast_1d(s[k]).astype(np.float32)))
-        out[k] = buf.to(self._device, non_blocking=True)
+        buf[i].copy_(torch.from_numpy(np.ascontiguousarray(np.atleast_1d(s[k]), dtype=np.float32)))
+      out[k] = buf.to(self._device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(self._device))
+    self._copied[slot] = ev
     return out

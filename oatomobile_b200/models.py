@@ -62,8 +62,13 @@ class _EncoderModel(nn.Module):
     if "lidar" in sample:
       sample["visual_features"] = sample.pop("lidar")
     if "visual_features" in sample:
-      sample["visual_features"] = transforms.downsample_and_transpose_visual_features(
-          sample["visual_features"])
+      v = sample["visual_features"]
+      if v.dim() == 4 and v.shape[-1] <= 8 < v.shape[1] and v.shape[1] == v.shape[2]:
+        # extension: [B,H,W,C] as stored on disk / delivered by the simulator
+        # (`DeviceCollator`) -> HWC->CHW fused into the resize kernel
+        sample["visual_features"] = transforms.downsample_and_transpose_visual_features_hwc(v)
+      else:
+        sample["visual_features"] = transforms.downsample_and_transpose_visual_features(v)
     return sample
 
 

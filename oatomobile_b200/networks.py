@@ -23,12 +23,6 @@ _MBV2_SETTING = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2),
                  (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1))
 
 
-def _native_only(name):
-  raise N.NativeLibraryError(
-      "%s holds parameters only; its arithmetic runs inside the fused CUDA path "
-      "(ImitativeModel._params / BehaviouralModel.forward)." % name)
-
-
 class _ConvBNReLU(nn.Sequential):
 
   def __init__(self, cin, cout, kernel_size=3, stride=1, groups=1):
@@ -90,8 +84,23 @@ class MobileNetV2(nn.Module):
     self._model.features[0][0] = nn.Conv2d(in_channels, 32, kernel_size=3, stride=2, padding=1,
                                            bias=False)
 
+    self._num_classes = num_classes
+    object.__setattr__(self, "_cache", None)
+    object.__setattr__(self, "_ens", None)
+
   def forward(self, x: torch.Tensor) -> torch.Tensor:
-    _native_only("MobileNetV2")
+    """perception.py:53-55 — x [B,C,100,100] -> [B,num_classes], eval-mode arithmetic (folded
+    BatchNorm running statistics, Dropout = identity) through `oat_encode_features`.  The CUDA
+    encoder is specialised for the shapes of this path: 100x100 inputs and 128 classes."""
+    if self._num_classes != 128:
+      raise N.NativeLibraryError("the CUDA encoder is specialised for num_classes=128 "
+                                 "(dim/model.py:53), got %d" % self._num_classes)
+    if self._cache is None:
+      object.__setattr__(self, "_cache", _HandleCache(self, N.KIND_ENCODER))
+    h = self._cache.get()
+    if self._ens is None or self._ens.models[0] is not h:
+      object.__setattr__(self, "_ens", N.EnsembleHandle([h]))
+    return ops.encode_features(self._ens, x)[0]
 
 
 class MLP(nn.Module):
@@ -113,8 +122,21 @@ class MLP(nn.Module):
       layers.append(activation_fn(inplace=True))
     self._model = nn.Sequential(*layers)
 
+    self._activate_final = activate_final
+    if activation_fn is not nn.ReLU or dropout_rate is not None:
+      self._unsupported = "activation_fn=%s, dropout_rate=%s" % (getattr(activation_fn, "__name__", activation_fn), dropout_rate)
+    else:
+      self._unsupported = None
+
   def forward(self, x: torch.Tensor) -> torch.Tensor:
-    _native_only("MLP")
+    """mlp.py:70-72 — one fused launch (`oat_mlp_forward`) over the module's own parameters.
+    Only the configuration this path uses has a kernel: ReLU activations, no dropout."""
+    if self._unsupported:
+      raise N.NativeLibraryError("MLP.forward: no CUDA kernel for %s (ReLU stacks without "
+                                 "dropout only)" % self._unsupported)
+    linears = [m for m in self._model if isinstance(m, nn.Linear)]
+    return ops.mlp_forward([l.weight for l in linears], [l.bias for l in linears], x,
+                           self._activate_final)
 
 
 class _HandleCache:

@@ -45,11 +45,57 @@ def encode(ens: N.EnsembleHandle, visual: torch.Tensor, scalars: torch.Tensor) -
   if tuple(visual.shape[2:]) != (100, 100):
     raise ValueError("`visual_features` must be [B,C,100,100] (apply `model.transform` first), "
                      "got %s" % (tuple(visual.shape),))
+  # the C call receives only B: a wrong channel count or scalar width would be read
+  # mis-strided / out of bounds, so both are checked here against the packed model
+  if visual.shape[1] != ens.in_channels:
+    raise ValueError("`visual_features` has %d channels, the model's stem expects %d"
+                     % (visual.shape[1], ens.in_channels))
+  if tuple(scalars.shape) != (B, ens.scalars):
+    raise ValueError("context scalars must concatenate to [B,%d], got %s"
+                     % (ens.scalars, tuple(scalars.shape)))
   z = torch.empty(len(ens), B, 64, device=visual.device, dtype=torch.float32)
   with torch.cuda.device(visual.device):
     N.check(N.lib().oat_encode(ens.ptr, visual.data_ptr(), scalars.data_ptr(), B, z.data_ptr(),
                                N.stream_ptr(visual.device)))
   return z
+
+
+def encode_features(ens: N.EnsembleHandle, visual: torch.Tensor) -> torch.Tensor:
+  """perception.py:53-55 for all E models: visual [B,C,100,100] -> features [E,B,128]."""
+  visual = N.require_cuda_f32(visual, "x")
+  B = visual.shape[0]
+  if visual.dim() != 4 or tuple(visual.shape[2:]) != (100, 100):
+    raise ValueError("the CUDA encoder is specialised for [B,C,100,100] inputs (the size "
+                     "`ImitativeModel.transform` produces), got %s" % (tuple(visual.shape),))
+  if visual.shape[1] != ens.in_channels:
+    raise ValueError("input has %d channels, the stem expects %d" % (visual.shape[1], ens.in_channels))
+  feat = torch.empty(len(ens), B, 128, device=visual.device, dtype=torch.float32)
+  with torch.cuda.device(visual.device):
+    N.check(N.lib().oat_encode_features(ens.ptr, visual.data_ptr(), B, feat.data_ptr(),
+                                        N.stream_ptr(visual.device)))
+  return feat
+
+
+def mlp_forward(weights, biases, x: torch.Tensor, activate_final: bool) -> torch.Tensor:
+  """mlp.py:70-72 for a Linear/ReLU stack: `weights[l]` [out,in], `biases[l]` [out] (device)."""
+  import ctypes
+  x = N.require_cuda_f32(x, "x")
+  lead = x.shape[:-1]
+  x2 = x.reshape(-1, x.shape[-1])
+  ws = [N.require_cuda_f32(w, "weight") for w in weights]
+  bs = [None if b is None else N.require_cuda_f32(b, "bias") for b in biases]
+  sizes = [ws[0].shape[1]] + [w.shape[0] for w in ws]
+  if x2.shape[1] != sizes[0] or any(ws[l].shape[1] != sizes[l] for l in range(len(ws))):
+    raise ValueError("MLP: input / layer widths do not chain: %s vs input %d" % (sizes, x2.shape[1]))
+  out = torch.empty(x2.shape[0], sizes[-1], device=x.device, dtype=torch.float32)
+  vp = ctypes.c_void_p
+  w_arr = (vp * len(ws))(*[w.data_ptr() for w in ws])
+  b_arr = (vp * len(ws))(*[None if b is None else b.data_ptr() for b in bs])
+  s_arr = (ctypes.c_int32 * len(sizes))(*sizes)
+  with torch.cuda.device(x.device):
+    N.check(N.lib().oat_mlp_forward(w_arr, b_arr, s_arr, len(ws), 1 if activate_final else 0,
+                                    x2.data_ptr(), x2.shape[0], out.data_ptr(), N.stream_ptr(x.device)))
+  return out.reshape(*lead, sizes[-1])
 
 
 # (h, c) of the activation after `blocks` inverted-residual blocks (0 = stem)

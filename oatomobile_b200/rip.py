@@ -66,6 +66,7 @@ class RIPScorer:
     self._graph_misses = 0
     self._graph_max_batch = 0
     self._vis_buf = None
+    self._ctx_bufs = {}
     self.replayed_launches = 0  # kernel launches executed through graph replays
 
   def _mark(self, name: str) -> None:
@@ -81,6 +82,7 @@ class RIPScorer:
     if key != self._ens_key:
       self._ens = N.EnsembleHandle(handles)
       self._ens_key = key
+      self._graphs.clear()  # graphs captured against the old packed weights must never replay
     return self._ens
 
   @property
@@ -88,30 +90,42 @@ class RIPScorer:
     return len(self._models)
 
   # ---- stages ----------------------------------------------------------------
-  def encode(self, **context: torch.Tensor) -> torch.Tensor:
-    """E_local x `_params` in grouped launches → z [E_local,B,64]."""
-    _require(context, _CONTEXT_KEYS)
+  def encode(self, scalars: Optional[torch.Tensor] = None, **context: torch.Tensor) -> torch.Tensor:
+    """E_local x `_params` in grouped launches → z [E_local,B,64].  `scalars` (optional): the
+    vector inputs already concatenated to one contiguous [B,5] buffer (replaces the three keys)."""
+    if scalars is None:
+      _require(context, _CONTEXT_KEYS)
+    elif "visual_features" not in context:
+      raise ValueError("Missing `visual_features` keyword argument.")
     if not self._use_graphs:
       return ops.encode(self._ensemble(), context["visual_features"],
-                        _scalars(context, _CONTEXT_KEYS[1:]))
-    return self._encode_graphed(context)
+                        _scalars(context, _CONTEXT_KEYS[1:]) if scalars is None else scalars)
+    return self._encode_graphed(context, scalars)
 
-  def _encode_graphed(self, context) -> torch.Tensor:
+  def _encode_graphed(self, context, scalars=None) -> torch.Tensor:
     """The encoder stage as one CUDA-graph replay.  The graph bakes in the input pointers,
     the ensemble's activation workspace and the TMA descriptors, so it is keyed by the input
     buffers and dropped whenever a larger batch makes the workspace grow."""
     ens = self._ensemble()
-    tensors = [N.require_cuda_f32(context[k], k) for k in _CONTEXT_KEYS]
+    if scalars is None:
+      tensors = [N.require_cuda_f32(context[k], k) for k in _CONTEXT_KEYS]
+    else:
+      tensors = [N.require_cuda_f32(context["visual_features"], "visual_features"),
+                 N.require_cuda_f32(scalars, "scalars")]
     batch = tensors[0].shape[0]
     if batch > self._graph_max_batch:  # `oat_ensemble_reserve` reallocates: old graphs dangle
       self._graphs.clear()
       self._graph_max_batch = batch
-    key = (id(ens),) + tuple((t.data_ptr(), tuple(t.shape)) for t in tensors)
+    # `generation` is a process-wide counter (id() of a freed ensemble can be reused)
+    key = (ens.generation,) + tuple((t.data_ptr(), tuple(t.shape)) for t in tensors)
     entry = self._graphs.get(key)
     if entry is None:
       self._graph_misses += 1
-      ctx = dict(zip(_CONTEXT_KEYS, tensors))
-      run = lambda: ops.encode(ens, ctx["visual_features"], _scalars(ctx, _CONTEXT_KEYS[1:]))
+      if scalars is None:
+        ctx = dict(zip(_CONTEXT_KEYS, tensors))
+        run = lambda: ops.encode(ens, ctx["visual_features"], _scalars(ctx, _CONTEXT_KEYS[1:]))
+      else:
+        run = lambda: ops.encode(ens, tensors[0], tensors[1])
       z = run()  # un-captured first: workspace reservation, kernel attributes, lazy init
       if self._graph_misses > self._MAX_GRAPH_MISSES:
         self._use_graphs = False  # the caller does not reuse its buffers: plain launches
@@ -150,8 +164,9 @@ class RIPScorer:
     return self._vis_buf
 
   def score(self, z: torch.Tensor, x: torch.Tensor, goal: Optional[torch.Tensor] = None,
-            epsilon: float = 1.0, want_s: bool = False) -> Dict[str, torch.Tensor]:
-    """z [E_local,B,64], x [B,K,T,2] → plan/kstar/sbest (+ y, q, s)."""
+            epsilon: float = 1.0, want_s: bool = False, x_is_local: bool = False) -> Dict[str, torch.Tensor]:
+    """z [E_local,B,64], x [B,K,T,2] → plan/kstar/sbest (+ y, q, s).  With `x_is_local` (sharded
+    ensembles) `x` holds only this rank's B/R scenes — the ones whose proposals it decodes."""
     ens = self._ensemble()
     self._mark("flow_begin")
     if self._world == 1:
@@ -162,17 +177,18 @@ class RIPScorer:
       # (1) z_0 from the owner of model 0 (64 floats per scene).
       z0 = z[0].contiguous() if self._rank == 0 else torch.empty_like(z[0])
       dist.broadcast(z0, src=dist.get_global_rank(self._group, 0), group=self._group)
-      Bn, Kn, Tn = x.shape[0], x.shape[1], x.shape[2]
-      if Bn % self._world == 0:
+      Bn, Kn, Tn = z.shape[1], x.shape[1], x.shape[2]
+      if x_is_local or Bn % self._world == 0:
         # (2) proposals: 1/R of the scenes per rank through the replicated decoder of model 0,
         # all-gathered over NVLink.  Measured before (every rank but 0 decoding ALL rows, then
         # scoring): the flow stage of ranks != 0 cost 2x rank 0's at one model per rank.
         n = Bn // self._world
         lo = self._rank * n
         prop = self._models[0] if self._rank == 0 else self._proposal_model
-        y_part, _ = ops.flow_forward(prop._decoder._handle(), x[lo:lo + n].reshape(-1, Tn, 2),
+        x_loc = x if x_is_local else x[lo:lo + n]
+        y_part, _ = ops.flow_forward(prop._decoder._handle(), x_loc.reshape(-1, Tn, 2),
                                      z0[lo:lo + n], rows_per_z=Kn)
-        y = torch.empty_like(x)
+        y = torch.empty((Bn, Kn, Tn, 2), device=x.device, dtype=x.dtype)
         dist.all_gather_into_tensor(y, y_part.view(n, Kn, Tn, 2).contiguous(), group=self._group)
         _, q = ops.rip_sample_score(ens, z, None, goal, epsilon, proposal_idx=-1, y=y)
       elif self._rank == 0:
@@ -197,11 +213,61 @@ class RIPScorer:
       out["s"] = s
     return out
 
+  def _gather_local_context(self, context, goal):
+    """Sharded inputs: every rank holds the context of its own B/R scenes.  The grids are
+    resized locally and the 4x smaller `visual_features` all-gathered ONCE; the vector inputs
+    and the goals travel in one packed all-gather (a few KB)."""
+    import torch.distributed as dist
+    R = self._world
+    part = ops.transform_visual(context["lidar"])
+    n = part.shape[0]
+    shape = (n * R,) + tuple(part.shape[1:])
+    vis = self._vis_buf if self._use_graphs else None
+    if vis is None or tuple(vis.shape) != shape or vis.device != part.device:
+      vis = torch.empty(shape, device=part.device, dtype=part.dtype)
+      if self._use_graphs:
+        self._vis_buf = vis
+    dist.all_gather_into_tensor(vis, part, group=self._group)
+    small = [context[k].reshape(n, -1).float() for k in _CONTEXT_KEYS[1:]]
+    if goal is not None:
+      small.append(goal.reshape(n, -1).float())
+    packed = torch.cat(small, dim=1).contiguous()
+    S = sum(t.shape[1] for t in small[:3])
+    # the gathered context feeds the encoder graph: persistent buffers per shape
+    key = (n * R, packed.shape[1])
+    bufs = self._ctx_bufs.get(key)
+    if bufs is None:
+      mk = lambda w: torch.empty((n * R, w), device=packed.device, dtype=torch.float32)
+      bufs = (mk(packed.shape[1]), mk(S), mk(max(packed.shape[1] - S, 1)))
+      self._ctx_bufs = {key: bufs}
+    allp, scal, gbuf = bufs
+    dist.all_gather_into_tensor(allp, packed, group=self._group)
+    scal.copy_(allp[:, :S])
+    goal_all = None
+    if goal is not None:
+      gbuf.copy_(allp[:, S:])
+      goal_all = gbuf.view(n * R, goal.shape[1], 2)
+    return vis, scal, goal_all
+
   def __call__(self, x: torch.Tensor, goal: Optional[torch.Tensor] = None, epsilon: float = 1.0,
-               want_s: bool = False, **context: torch.Tensor) -> Dict[str, torch.Tensor]:
+               want_s: bool = False, local_slice: bool = False,
+               **context: torch.Tensor) -> Dict[str, torch.Tensor]:
     """Full step of the metric on device-resident inputs.  `context` holds either
-    `lidar` [B,C,200,200] (raw) or `visual_features` [B,C,100,100] (transformed)."""
+    `lidar` [B,C,200,200] (raw) or `visual_features` [B,C,100,100] (transformed).
+
+    `local_slice=True` (sharded ensembles): `lidar`, `x`, `goal` and the vector inputs hold only
+    THIS rank's B/R scenes (rank r owns scenes [r*B/R, (r+1)*B/R) of the group's batch) — what a
+    rank-local feed delivers; nothing but the resized grids and a packed few-KB context crosses
+    NVLink before the encoder."""
     self._mark("step_begin")
+    if local_slice and self._world > 1:
+      vis, scal, goal = self._gather_local_context(context, goal)
+      self._mark("encode_begin")
+      z = self.encode(scalars=scal, visual_features=vis)
+      self._mark("encode_end")
+      out = self.score(z, x, goal, epsilon, want_s, x_is_local=True)
+      out["z"] = z
+      return out
     if "lidar" in context:
       context = dict(context)
       lidar = context.pop("lidar")
@@ -247,6 +313,7 @@ class HostRIPPipeline:
     self._dev = [{}, {}]            # double-buffered device inputs
     self._host_out = {}
     self._copy_stream = torch.cuda.Stream(device=self._device)
+    self._sharded = [False, False]  # per slot: inputs hold only this rank's 1/R scene slice
     self._uploaded = [torch.cuda.Event(), torch.cuda.Event()]
     self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
     self.h2d_bytes = 0
@@ -255,40 +322,42 @@ class HostRIPPipeline:
   def _upload(self, host, lo, hi, slot):
     """Async H2D of scenes [lo,hi) into buffer `slot` on the copy stream.
 
-    When the ensemble is sharded over R ranks every rank needs every scene, but each rank
-    pulls only its 1/R slice over PCIe; `_assemble` then all-gathers the slices over NVLink."""
+    When the ensemble is sharded over R ranks each rank pulls only its 1/R slice of the
+    scenes over PCIe into compact [n,...] buffers; the scorer (`local_slice=True`) resizes the
+    local grids and all-gathers only `visual_features` plus a packed few-KB context.  The
+    decision is stored PER SLOT: slice i+1 is uploaded before slice i is consumed."""
     h2d = 0
     R, r = self._scorer._world, self._scorer._rank
     shard = R > 1 and (hi - lo) % R == 0
+    n = (hi - lo) // R if shard else hi - lo
+    a = lo + r * n if shard else lo
     with torch.cuda.stream(self._copy_stream):
       self._copy_stream.wait_event(self._consumed[slot])  # previous user of the slot is done
       for k in self.INPUT_KEYS:
-        src = host[k][lo:hi]
+        src = host[k][a:a + n]
         buf = self._dev[slot].get(k)
         if buf is None or buf.shape != src.shape:
           buf = torch.empty(src.shape, dtype=torch.float32, device=self._device)
           self._dev[slot][k] = buf
-        if shard:
-          n = (hi - lo) // R
-          buf[r * n:(r + 1) * n].copy_(src[r * n:(r + 1) * n], non_blocking=True)
-          h2d += src[r * n:(r + 1) * n].numel() * 4
-        else:
-          buf.copy_(src, non_blocking=True)
-          h2d += src.numel() * 4
+        buf.copy_(src, non_blocking=True)
+        h2d += src.numel() * 4
       self._uploaded[slot].record(self._copy_stream)
-    self._sharded = shard
+    self._sharded[slot] = shard
     return h2d
 
-  def _assemble(self, slot):
-    """Sharded uploads: all-gather every input in place (compute stream, NCCL/NVLink)."""
-    if not getattr(self, "_sharded", False):
-      return
-    import torch.distributed as dist
+  def _score_slot(self, slot, epsilon):
+    d = dict(self._dev[slot])
+    x, goal = d.pop("x"), d.pop("goal")
+    return self._scorer(x=x, goal=goal, epsilon=epsilon, local_slice=self._sharded[slot], **d)
+
+  def _result_rows(self, slot, lo, hi):
+    """Host rows this rank reads back: with sharded inputs its own scenes only (every rank holds
+    the same full result on the device; the feed that delivered scene b gets plan b)."""
+    if not self._sharded[slot]:
+      return lo, hi, 0, hi - lo
     R, r = self._scorer._world, self._scorer._rank
-    for k in self.INPUT_KEYS:
-      buf = self._dev[slot][k]
-      n = buf.shape[0] // R
-      dist.all_gather_into_tensor(buf, buf[r * n:(r + 1) * n].clone(), group=self._scorer._group)
+    n = (hi - lo) // R
+    return lo + r * n, lo + (r + 1) * n, r * n, (r + 1) * n
 
   def __call__(self, host: Dict[str, torch.Tensor], epsilon: float = 1.0):
     B = host["lidar"].shape[0]
@@ -310,14 +379,12 @@ class HostRIPPipeline:
       if i + 1 < n:  # prefetch the next slice while this one is scored
         h2d += self._upload(host, bounds[i + 1][0], bounds[i + 1][1], slot ^ 1)
       compute.wait_event(self._uploaded[slot])
-      self._assemble(slot)
-      d = dict(self._dev[slot])
-      x, goal = d.pop("x"), d.pop("goal")
-      out = self._scorer(x=x, goal=goal, epsilon=epsilon, **d)
+      out = self._score_slot(slot, epsilon)
       self._consumed[slot].record(compute)
+      h0, h1, d0, d1 = self._result_rows(slot, lo, hi)
       for k in ("plan", "kstar", "sbest"):
-        self._host_out[k][lo:hi].copy_(out[k], non_blocking=True)
-        d2h += out[k].numel() * out[k].element_size()
+        self._host_out[k][h0:h1].copy_(out[k][d0:d1], non_blocking=True)
+        d2h += out[k][d0:d1].numel() * out[k].element_size()
     compute.synchronize()  # results are now valid on the host
     self.h2d_bytes, self.d2h_bytes = h2d, d2h
     return {k: self._host_out[k] for k in ("plan", "kstar", "sbest")}
@@ -335,16 +402,15 @@ class HostRIPPipeline:
 
     def enqueue(batch, slot):
       """upload + score + async D2H of one batch; returns (results, done event)."""
-      h2d = self._upload(batch, 0, batch["lidar"].shape[0], slot)
+      nb = batch["lidar"].shape[0]
+      h2d = self._upload(batch, 0, nb, slot)
       compute.wait_event(self._uploaded[slot])
-      self._assemble(slot)
-      d = dict(self._dev[slot])
-      x, goal = d.pop("x"), d.pop("goal")
-      out = self._scorer(x=x, goal=goal, epsilon=epsilon, **d)
+      out = self._score_slot(slot, epsilon)
       self._consumed[slot].record(compute)
+      _, _, d0, d1 = self._result_rows(slot, 0, nb)
       d2h, res = 0, {}
       for k in ("plan", "kstar", "sbest"):
-        t = out[k]
+        t = out[k][d0:d1]
         hb = self._host_out.get((k, slot))
         if hb is None or hb.shape != t.shape:
           hb = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)

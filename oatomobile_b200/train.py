@@ -81,6 +81,8 @@ class Trainer:
     self.device = params[0].device
     self._flatten()
     self._bind()
+    if self.world > 1:
+      self.sync_replicas()
 
   # -- storage ------------------------------------------------------------------
   def _flatten(self):
@@ -127,6 +129,46 @@ class Trainer:
     self._bn_counters = [b for n, b in self.model.named_buffers() if n.endswith("num_batches_tracked")]
     self._bn_stats = [b for n, b in self.model.named_buffers() if "running_" in n]
 
+  def sync_replicas(self, src: int = 0) -> None:
+    """What DDP does at construction: every replica starts from rank `src`'s parameters and
+    BatchNorm buffers (ranks built with different seeds or checkpoints would otherwise drift
+    apart while still averaging gradients).  Also called after `load_state_dict`."""
+    if self.world <= 1:
+      return
+    g = dist.get_global_rank(self.group, src) if self.group is not None else src
+    dist.broadcast(self.flat, src=g, group=self.group)
+    for b in self._bn_stats + self._bn_counters:
+      dist.broadcast(b, src=g, group=self.group)
+    for t in (self.exp_avg, self.exp_avg_sq):
+      dist.broadcast(t, src=g, group=self.group)
+    step = torch.tensor([self.step_count], device=self.device, dtype=torch.int64)
+    dist.broadcast(step, src=g, group=self.group)
+    self.step_count = int(step.item())
+    _bump_versions([p for _, p in self._named] + self._bn_stats)
+
+  # -- optimiser state (the reference checkpoints only the model, savers.py:39-55; resuming
+  #    Adam needs its moments and step, so they are exposed in `torch.optim` form) ---------
+  def state_dict(self):
+    """{"step", "exp_avg", "exp_avg_sq"}: moments keyed by parameter name (clones)."""
+    out = {"step": self.step_count, "exp_avg": {}, "exp_avg_sq": {}}
+    off = 0
+    for name, p in self._named:
+      n = p.numel()
+      out["exp_avg"][name] = self.exp_avg[off:off + n].view(p.shape).clone()
+      out["exp_avg_sq"][name] = self.exp_avg_sq[off:off + n].view(p.shape).clone()
+      off += (n + 3) // 4 * 4
+    return out
+
+  def load_state_dict(self, state) -> None:
+    self.step_count = int(state["step"])
+    off = 0
+    with torch.no_grad():
+      for name, p in self._named:
+        n = p.numel()
+        self.exp_avg[off:off + n].copy_(state["exp_avg"][name].reshape(-1))
+        self.exp_avg_sq[off:off + n].copy_(state["exp_avg_sq"][name].reshape(-1))
+        off += (n + 3) // 4 * 4
+
   def __del__(self):
     try:
       if getattr(self, "_ptr", None):
@@ -148,6 +190,13 @@ class Trainer:
     B, T = target.shape[0], target.shape[1]
     if visual.shape[0] != B or tuple(visual.shape[2:]) != (100, 100):
       raise ValueError("visual_features must be [B,C,100,100] (apply `model.transform` first)")
+    in_channels = self.model._encoder._model.features[0][0].in_channels
+    if visual.shape[1] != in_channels:
+      raise ValueError("visual_features has %d channels, the model's stem expects %d"
+                       % (visual.shape[1], in_channels))
+    if tuple(scalars.shape) != (B, len(self._keys) + 2):
+      raise ValueError("context scalars must concatenate to [B,%d] (%s), got %s"
+                       % (len(self._keys) + 2, ", ".join(self._keys), tuple(scalars.shape)))
     if isinstance(dropout_mask, str):
       keep = 1.0 - self.model._encoder._model.classifier[0].p
       dropout_mask = torch.bernoulli(torch.full((B, 1280), keep, device=self.device)) / keep

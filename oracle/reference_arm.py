@@ -76,7 +76,7 @@ def rip_score(models, lidar, velocity, is_at_traffic_light, traffic_light_state,
     zs = [m._params(**ctx) for m in models]                               # rip/agent.py:93
     rep = lambda z: z.repeat_interleave(K, dim=0)
     y, _ = models[0]._decoder._forward(x.reshape(B * K, T, 2), rep(zs[0]))  # rip/agent.py:106
-    q = torch.empty(len(models), B, K)
+    q = torch.empty(len(models), B, K, device=x.device)
     for m, (model, z) in enumerate(zip(models, zs)):                      # rip/agent.py:109-112
       _, log_prob, logabsdet = model._decoder._inverse(y, rep(z))
       q[m] = (log_prob - logabsdet).view(B, K)
@@ -84,7 +84,7 @@ def rip_score(models, lidar, velocity, is_at_traffic_light, traffic_light_state,
     if goal is not None:
       g = goal.repeat_interleave(K, dim=0)                                # [B*K,G,2]
       dist = D.MixtureSameFamily(                                         # dim/model.py:163-169
-          mixture_distribution=D.Categorical(probs=torch.ones(g.shape[:2])),
+          mixture_distribution=D.Categorical(probs=torch.ones(g.shape[:2], device=g.device)),
           component_distribution=D.Independent(
               D.Normal(loc=g, scale=torch.ones_like(g) * epsilon), reinterpreted_batch_ndims=1))
       q = q + dist.log_prob(y[:, :, -1, :].reshape(B * K, 2)).view(1, B, K)
@@ -95,6 +95,7 @@ def rip_score(models, lidar, velocity, is_at_traffic_light, traffic_light_state,
     else:
       s = torch.mean(-q, dim=0)
     kstar = torch.argmin(s, dim=1)
-    plan = y[torch.arange(B), kstar]
+    rows = torch.arange(B, device=x.device)
+    plan = y[rows, kstar]
   return dict(z=torch.stack(zs), y=y, q=q, s=s, kstar=kstar, plan=plan,
-              sbest=s[torch.arange(B), kstar])
+              sbest=s[rows, kstar])

@@ -358,12 +358,13 @@ def _adam_step(x, grad, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
 
 def planner(sds: Sequence[StateDict], zs: Sequence[Tensor], x0: Tensor, num_steps: int,
             lr: float, goal: Optional[Tensor], epsilon: float,
-            algorithm: Optional[str]) -> Tuple[Tensor, Tensor]:
+            algorithm: Optional[str], trace: Optional[dict] = None) -> Tuple[Tensor, Tensor]:
   """Shared restatement of the two Adam-on-latent planners.
 
   dim/model.py:117-139 (single model, ``algorithm=None``) and rip/agent.py:102-137
   (ensemble).  Quirk kept: ``x_best`` is the *post-step* x (dim/model.py:133-137).
-  Returns (plan y [B,T,2], x_best).
+  Returns (plan y [B,T,2], x_best).  `trace` (a dict) receives the per-step losses and the
+  first-step gradient, for tests that pin per-step quantities.
   """
   x = x0.clone()
   m = torch.zeros_like(x)
@@ -390,6 +391,10 @@ def planner(sds: Sequence[StateDict], zs: Sequence[Tensor], x0: Tensor, num_step
     else:
       loss = torch.mean(-P, dim=0)
     (grad,) = torch.autograd.grad(loss, xg)
+    if trace is not None:
+      trace.setdefault("losses", []).append(float(loss.detach()))
+      if step == 1:
+        trace["grad1"] = grad.detach().clone()
     x = _adam_step(x, grad, m, v, step, lr)
     if loss.detach() < loss_best:
       x_best = x.clone()

@@ -38,6 +38,8 @@ CONFIGS = {
     # name: (T, C, E, B, K, weight seed base, input seed)
     "dim_T4_C2": dict(T=4, C=2, E=3, B=2, K=8, wseed=100, iseed=0),
     "dim_T10_C4": dict(T=10, C=4, E=4, B=2, K=16, wseed=200, iseed=5),
+    # the metric's own sample count per scene (BASELINE configs[2]: K=512, T=10, C=4, E=4)
+    "dim_T10_C4_K512": dict(T=10, C=4, E=4, B=2, K=512, wseed=100, iseed=6),
 }
 
 

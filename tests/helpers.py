@@ -12,6 +12,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CONFIGS = {
     "dim_T4_C2": dict(T=4, C=2, E=3, B=2, K=8, wseed=100, iseed=0),
     "dim_T10_C4": dict(T=10, C=4, E=4, B=2, K=16, wseed=200, iseed=5),
+    # the metric's own sample count per scene (BASELINE configs[2]: K=512, T=10, C=4, E=4)
+    "dim_T10_C4_K512": dict(T=10, C=4, E=4, B=2, K=512, wseed=100, iseed=6),
 }
 
 # north_star: "within 1e-4 relative on log-probs and waypoint means"
@@ -28,6 +30,9 @@ def fixture(cfg):
   return inp, sds
 
 
+ACHIEVED = {}  # what -> (largest relative error seen, the bar it was held to)
+
+
 def assert_close(actual, expected, tol=REL_TOL, what=""):
   """|a-b| <= tol * max(|a|,|b|,1) elementwise (SURVEY.md §8(d) parity bar)."""
   a = torch.as_tensor(np.asarray(actual.detach().cpu() if torch.is_tensor(actual) else actual),
@@ -38,6 +43,9 @@ def assert_close(actual, expected, tol=REL_TOL, what=""):
   scale = torch.maximum(torch.maximum(a.abs(), b.abs()), torch.ones_like(a))
   err = ((a - b).abs() / scale)
   worst = err.max().item() if err.numel() else 0.0
+  if what:
+    prev = ACHIEVED.get(what, (0.0, tol))
+    ACHIEVED[what] = (max(prev[0], worst), tol)
   assert worst <= tol, "%s: max rel err %.3e > %.1e" % (what, worst, tol)
   return worst
 

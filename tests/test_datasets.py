@@ -66,13 +66,30 @@ def test_load_datum_matches_reference(tmp_path):
 
 
 @pytest.mark.gpu
-def test_device_collator_matches_model_transform(tmp_path):
+def test_device_collator_then_model_transform_is_the_documented_loop(tmp_path):
+  """collate -> `model.transform(batch)` (dim/train.py:176-178) must transform the
+  grid exactly ONCE and leave a batch both train paths accept (T targets, CIL mode remap)."""
   import oatomobile_b200 as ob
   files = _write_samples(str(tmp_path))
   samples = [CARLADataset.load_datum(f, MODALITIES, mode=True, dataformat="HWC") for f in files]
-  batch = DeviceCollator("cuda:0")(samples)
-  model = ob.ImitativeModel(output_shape=(4, 2))
+  collate = DeviceCollator("cuda:0")
+  raw = collate(samples)
+  assert "visual_features" not in raw and tuple(raw["lidar"].shape) == (3, 200, 200, 2)
   chw = torch.stack([torch.from_numpy(np.transpose(s["lidar"], (2, 0, 1))) for s in samples]).cuda()
-  ref = model.transform({"lidar": chw})["visual_features"]
-  assert torch.equal(batch["visual_features"], ref)
-  assert tuple(batch["player_future"].shape) == (3, 80, 3)
+  for model in (ob.ImitativeModel(output_shape=(4, 2)), ob.BehaviouralModel(output_shape=(4, 2))):
+    batch = model.transform(collate(samples))
+    ref = model.transform({"lidar": chw.clone()})["visual_features"]
+    assert torch.equal(batch["visual_features"], ref)          # CHW reference path, same bits
+    assert tuple(batch["visual_features"].shape) == (3, 2, 100, 100)
+    assert tuple(batch["player_future"].shape) == (3, 4, 3)     # num_timesteps_to_keep = T
+    if isinstance(model, ob.BehaviouralModel):
+      assert not bool((batch["mode"] == 1.0).any())             # cil/model.py:161-163
+  # double-buffered pinned staging: batches stay intact while later collates run un-synchronised
+  outs = []
+  for i in range(5):
+    mod = [dict(s, velocity=s["velocity"] + i) for s in samples]
+    outs.append((i, collate(mod)["velocity"]))
+  torch.cuda.synchronize()
+  for i, v in outs:
+    want = torch.stack([torch.from_numpy(s["velocity"] + i) for s in samples])
+    assert torch.equal(v.cpu(), want), i

@@ -128,6 +128,17 @@ def _worker(rank, world, port, algo, out_path):
                                   inp["traffic_light_state"], inp["x"], inp["goal"], 1.0, algo)
   ok = (torch.equal(out["q"], ref["q"]) and torch.equal(out["s"], ref["s"]) and
         torch.equal(out["kstar"].long(), ref["kstar"]) and torch.equal(out["plan"], ref["plan"]))
+  if algo == "WCM":
+    # rank-local feed (`local_slice=True`, what HostRIPPipeline uploads): each rank passes only
+    # its B/R scenes; grids are resized locally, visual features + packed context all-gathered
+    n = inp["lidar"].shape[0] // world
+    sl = slice(rank * n, (rank + 1) * n)
+    with torch.no_grad():
+      loc = scorer(x=inp["x"][sl], goal=inp["goal"][sl], epsilon=1.0, want_s=True, local_slice=True,
+                   lidar=inp["lidar"][sl], velocity=inp["velocity"][sl],
+                   is_at_traffic_light=inp["is_at_traffic_light"][sl],
+                   traffic_light_state=inp["traffic_light_state"][sl])
+    ok = ok and all(torch.equal(loc[k], out[k]) for k in ("q", "s", "kstar", "plan", "y", "z"))
   # every rank must hold the same selection
   ks = [torch.empty_like(out["kstar"]) for _ in range(world)]
   dist.all_gather(ks, out["kstar"])

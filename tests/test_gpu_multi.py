@@ -51,7 +51,26 @@ def _worker(rank, world, port, out_path):
   ref = single(x=x, goal=goal, want_s=True, **d)
   torch.cuda.synchronize()
   ok = all(torch.equal(out[k], ref[k]) for k in ("q", "s", "kstar", "plan", "y"))
-  torch.save({"ok": bool(ok)}, out_path % rank)
+  # rank-local feed: every rank passes only its B/R scenes (`local_slice=True`)
+  n = B // world
+  sl = slice(rank * n, (rank + 1) * n)
+  loc = sharded(x=x[sl], goal=goal[sl], want_s=True, local_slice=True,
+                **{k: v[sl] for k, v in d.items()})
+  ok_local = all(torch.equal(loc[k], ref[k]) for k in ("q", "s", "kstar", "plan", "y"))
+  # host pipeline with slices whose shard decision differs (B=9, chunks=2, R=2 ->
+  # slice 0 has 4 scenes (sharded), slice 1 has 5 (replicated)): results == single GPU
+  from oatomobile_b200.rip import HostRIPPipeline
+  inp9 = synthetic_inputs(9, C, K, T, seed=5)
+  host = {k: v.pin_memory() for k, v in inp9.items()}
+  d9 = {k: v.to(dev) for k, v in inp9.items()}
+  x9, g9 = d9.pop("x"), d9.pop("goal")
+  ref9 = single(x=x9, goal=g9, **d9)
+  res = HostRIPPipeline(sharded, dev, chunks=2)(host)
+  torch.cuda.synchronize()
+  rows = list(range(rank * 2, rank * 2 + 2)) + list(range(4, 9))  # own rows of slice 0 + all of slice 1
+  ok_pipe = (torch.equal(res["kstar"][rows], ref9["kstar"].cpu()[rows]) and
+             torch.equal(res["plan"][rows], ref9["plan"].cpu()[rows]))
+  torch.save({"ok": bool(ok), "ok_local": bool(ok_local), "ok_pipe": bool(ok_pipe)}, out_path % rank)
   dist.destroy_process_group()
 
 
@@ -61,7 +80,10 @@ def test_sharded_equals_single_gpu(tmp_path):
   out_path = str(tmp_path / "r%d.pt")
   mp.spawn(_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
   for r in range(2):
-    assert torch.load(out_path % r)["ok"], "rank %d differs from the single-GPU result" % r
+    res = torch.load(out_path % r)
+    assert res["ok"], "rank %d differs from the single-GPU result" % r
+    assert res["ok_local"], "rank %d: rank-local feed differs from the single-GPU result" % r
+    assert res["ok_pipe"], "rank %d: host pipeline (mixed shard decisions) differs" % r
 
 
 def _train_worker(rank, world, port, out_path):
@@ -93,7 +115,17 @@ def _train_worker(rank, world, port, out_path):
                 traffic_light_state=scalars[lo:hi, 4:5].to(dev)), target[lo:hi].to(dev)
 
   half = cfg["B"] // world
-  model, trainer = make(dist.new_group(list(range(world))))
+  group = dist.new_group(list(range(world)))
+  # replicas built from different weights must start from rank 0's (DDP's broadcast)
+  other = ob.ImitativeModel(output_shape=(cfg["T"], 2), in_channels=cfg["C"])
+  other.load_state_dict(synthetic_state_dict("dim", cfg["C"], cfg["wseed"] + 1 + rank), strict=True)
+  t_other = Trainer(other.to(dev), lr=1e-3, group=group)
+  flats = [torch.empty_like(t_other.flat) for _ in range(world)]
+  dist.all_gather(flats, t_other.flat)
+  bn0 = [torch.empty_like(t_other._bn_stats[0]) for _ in range(world)]
+  dist.all_gather(bn0, t_other._bn_stats[0])
+  synced = all(torch.equal(f, flats[0]) for f in flats) and all(torch.equal(b, bn0[0]) for b in bn0)
+  model, trainer = make(group)
   b, t = batch(rank * half, (rank + 1) * half)
   trainer.forward_backward(b, t, dropout_mask=None)
   trainer.optimizer_step()
@@ -112,7 +144,7 @@ def _train_worker(rank, world, port, out_path):
   dist.all_gather(gathered, trainer.flat)
   same_everywhere = all(torch.equal(g, gathered[0]) for g in gathered)
   diff = (trainer.flat - solo.flat).abs()
-  torch.save({"same": bool(same_everywhere), "err": float(diff.max()), "mean": float(diff.mean())},
+  torch.save({"synced": bool(synced), "same": bool(same_everywhere), "err": float(diff.max()), "mean": float(diff.mean())},
              out_path % rank)
   dist.destroy_process_group()
 
@@ -124,6 +156,7 @@ def test_data_parallel_train_step(tmp_path):
   mp.spawn(_train_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
   for r in range(2):
     res = torch.load(out_path % r)
+    assert res["synced"], "replicas built from different weights were not synchronised"
     assert res["same"], "ranks hold different parameters after the step"
     # Adam's first step is lr * g / (|g| + eps): for the entries whose true gradient is zero
     # (BatchNorm biases in front of another BatchNorm) the atomics' summation order decides

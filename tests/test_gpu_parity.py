@@ -230,7 +230,7 @@ def test_full_size_properties():
                                   y=out["y"])
   assert torch.equal(q_sep, out["q"])
   # a sampled subset of scenes against the oracle (full path from the raw grids)
-  idx = [0, 101, 255]
+  idx = list(range(0, B, 8))  # 32 of the 256 scenes (3 were too few)
   with torch.no_grad():
     ref = R.rip_score_from_inputs(sds, inp["lidar"][idx], inp["velocity"][idx],
                                   inp["is_at_traffic_light"][idx],
@@ -239,7 +239,15 @@ def test_full_size_properties():
   assert_close(out["z"][:, idx], ref["z"], REL_TOL, "z subset")
   assert_close(out["q"][:, idx], ref["q"], REL_TOL, "q subset")
   assert_close(out["y"][idx], ref["y"], REL_TOL, "y subset")
+  # selected index, judged on the ORACLE's own scores: the plan the GPU picked must be (within the
+  # value bar) as good as the oracle's best, whatever the gap; and identical when the gap is clear
   gap = top2_gap(ref["s"])
+  exact = 0
   for j, b in enumerate(idx):
-    if gap[j] > 10 * REL_TOL:
-      assert int(out["kstar"][b]) == int(ref["kstar"][j])
+    kg, kr = int(out["kstar"][b]), int(ref["kstar"][j])
+    s_g, s_r = float(ref["s"][j, kg]), float(ref["s"][j, kr])
+    assert s_g - s_r <= 2 * REL_TOL * max(1.0, abs(s_r)), (b, kg, kr, s_g, s_r)
+    if gap[j] > 2 * REL_TOL:
+      assert kg == kr, (b, kg, kr, float(gap[j]))
+      exact += 1
+  assert exact >= len(idx) // 2, "too few scenes with a clear top-2 gap to pin the index"

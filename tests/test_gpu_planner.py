@@ -9,9 +9,14 @@ from tests.helpers import GOLDEN_CONFIGS, assert_close, fixture, golden, observa
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-# 10-20 Adam steps on the latent amplify fp32 rounding differences (Adam normalises the
-# gradient); the reference's own CPU run differs from the CPU oracle by up to 1e-4.
+# End point after 10-20 Adam steps: Adam normalises the gradient (step = lr * m / sqrt(v)), so a
+# 1e-6 rounding difference in a near-zero gradient component moves x by a visible fraction of lr;
+# the reference's own CPU run differs from the CPU restatement by up to 1e-4 on these goldens.
+# The end point therefore keeps a 1e-3 bar, and the PER-STEP quantities (loss of every step, the
+# first-step gradient through its Adam update) are held to the north-star 1e-4 in
+# `test_planner_per_step_quantities`.  Achieved errors: gpurun_out/parity_achieved.json.
 PLAN_TOL = 1e-3
+STEP_TOL = 1e-4
 
 
 def _models(cfg, sds):
@@ -80,8 +85,43 @@ def test_cil_agent_call():
   assert_close(out, g["cil_agent"], 1e-4, "CILAgent")
 
 
+def test_planner_per_step_quantities():
+  """Per-step bars at 1e-4: the loss of each of the first steps and the first Adam update
+  (x_1 = x_0 - lr * sign-like(grad_1), i.e. the first-step gradient) against the autograd oracle."""
+  from oatomobile_b200 import ops
+  from oracle import restatement as R
+  cfg = GOLDEN_CONFIGS["dim_T4_C2"]
+  inp, sds = fixture(cfg)
+  models = _models(cfg, sds)
+  g = torch.Generator().manual_seed(15)
+  B, T, E = 3, cfg["T"], cfg["E"]
+  zs = [(torch.randn(B, 64, generator=g) * 0.4).clamp(min=0) for _ in range(E)]
+  goal = inp["goal"][:1].repeat(B, 1, 1) + torch.randn(B, 10, 2, generator=g) * 0.3
+  x0 = torch.randn(B, T, 2, generator=g) * 0.5
+  for algo in (None, "WCM", "BCM", "MA"):
+    n = 1 if algo is None else E
+    handles = [m.native_handle() for m in models[:n]]
+    zt = torch.stack(zs[:n]).to(DEV)
+    trace = {}
+    R.planner(sds[:n], zs[:n], x0, 3, 0.1, goal, 1.0, algo, trace=trace)
+    _, _, losses = ops.plan(handles, zt, x0.to(DEV), num_steps=3, lr=0.1, goal=goal.to(DEV),
+                            epsilon=1.0, algorithm=algo, want_loss=True)
+    assert_close(losses, torch.tensor(trace["losses"]), STEP_TOL, "planner loss trajectory (3 steps) %s" % algo)
+    # one step: x_best is the post-step x (dim/model.py:133-137), i.e. x_0 - lr * g / (|g| + eps)
+    ref1 = {}
+    _, xb_ref = R.planner(sds[:n], zs[:n], x0, 1, 0.1, goal, 1.0, algo, trace=ref1)
+    _, xb, l1 = ops.plan(handles, zt, x0.to(DEV), num_steps=1, lr=0.1, goal=goal.to(DEV), epsilon=1.0,
+                         algorithm=algo, want_loss=True)
+    assert_close(l1, torch.tensor(ref1["losses"]), 1e-5, "planner first loss %s" % algo)
+    # Adam's first step is lr * g / (|g| + eps): compare where the oracle's gradient is not at
+    # rounding level (a component within 1e-6 of zero may legitimately take the other sign)
+    clear = (ref1["grad1"].abs() > 1e-5).to(DEV)
+    assert bool(clear.float().mean() > 0.9)
+    assert_close(torch.where(clear, xb, xb_ref.to(DEV)), xb_ref, STEP_TOL, "planner first Adam update %s" % algo)
+
+
 def test_planner_matches_oracle_losses():
-  """Loss trajectory of the fused planner vs the autograd oracle, B > 1, every algorithm."""
+  """End points of the fused planner vs the autograd oracle, B > 1, every algorithm."""
   from oatomobile_b200 import ops
   from oracle import restatement as R
   cfg = GOLDEN_CONFIGS["dim_T4_C2"]
