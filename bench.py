@@ -430,7 +430,7 @@ def build_roofline(prof, psteps, work, peaks, clocks):
     rows[name] = row
   if not rows:
     return None
-  top = max(rows, key=lambda n: rows[n]["ms_per_step"])
+  top = max((n for n in rows if not n.startswith("(")), key=lambda n: rows[n]["ms_per_step"])
   r = rows[top]
   tensor = r["bound"] == "tensor"
   t = traffic.get(top)
@@ -814,7 +814,7 @@ def run_gpu_train(args):
       if not name:
         continue
       fam[name] = {"ms_per_step": p["ms"] / psteps, "launches_per_step": p["launches"] / psteps}
-      if top is None or fam[name]["ms_per_step"] > fam[top]["ms_per_step"]:
+      if not name.startswith("(") and (top is None or fam[name]["ms_per_step"] > fam[top]["ms_per_step"]):
         top = name
     # algorithmic flops of one training step: forward + dX + dW of every conv = 3x forward
     fwd = sum(layer_flops(l) for l in encoder_layers(C))

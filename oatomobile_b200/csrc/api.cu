@@ -583,6 +583,7 @@ int oat_transform_visual(const float* lidar, int32_t B, int32_t C, int32_t H, in
                          float* visual, void* stream) {
   if (B <= 0 || C <= 0) return 0;
   if (!lidar || !visual) return fail("oat_transform_visual: null pointer");
+  if (g_profile_on) profile_mark("(host gap before call)", (cudaStream_t)stream);
   if (H < 2 || W < 2) return fail("oat_transform_visual: input must be at least 2x2");
   return launch_transform_visual(lidar, B, C, H, W, visual, (cudaStream_t)stream);
 }
@@ -599,6 +600,7 @@ int oat_encode(OatEnsemble* ens, const float* visual, const float* scalars, int3
                void* stream) {
   if (B <= 0) return 0;
   if (!ens || !visual || !scalars || !z) return fail("oat_encode: null argument");
+  if (g_profile_on) profile_mark("(host gap before call)", (cudaStream_t)stream);
   if (int rc = check_device(ens->device, "oat_encode")) return rc;
   if (int rc = oat_ensemble_reserve(ens, B)) return rc;
   return encoder_forward(ens, visual, scalars, B, z, (cudaStream_t)stream);
@@ -663,6 +665,7 @@ int oat_flow_forward(const OatModel* model, const float* x, const float* z, int6
                      int32_t rows_per_z, float* y, float* logabsdet, void* stream) {
   if (N <= 0) return 0;
   if (!model || !x || !z || !y) return fail("oat_flow_forward: null argument");
+  if (g_profile_on) profile_mark("(host gap before call)", (cudaStream_t)stream);
   if (model->kind == OAT_KIND_CIL) return fail("oat_flow_forward: not a flow model");
   if (int rc = check_device(model->device, "oat_flow_forward")) return rc;
   FlowLaunch a{};
@@ -679,6 +682,7 @@ int oat_flow_inverse(const OatModel* model, const float* y, const float* z, int6
                      void* stream) {
   if (N <= 0) return 0;
   if (!model || !y || !z) return fail("oat_flow_inverse: null argument");
+  if (g_profile_on) profile_mark("(host gap before call)", (cudaStream_t)stream);
   if (model->kind == OAT_KIND_CIL) return fail("oat_flow_inverse: not a flow model");
   if (int rc = check_device(model->device, "oat_flow_inverse")) return rc;
   FlowLaunch a{};
@@ -695,6 +699,7 @@ int oat_rip_sample_score(OatEnsemble* ens, int32_t proposal_idx, const float* z,
                          int32_t T, float* y, float* q, void* stream) {
   if ((int64_t)B * K <= 0) return 0;
   if (!ens || !z || !y || !q) return fail("oat_rip_sample_score: null argument");
+  if (g_profile_on) profile_mark("(host gap before call)", (cudaStream_t)stream);
   const int E = (int)ens->models.size();
   if (proposal_idx >= E) return fail("oat_rip_sample_score: proposal_idx out of range");
   if (proposal_idx >= 0 && !x) return fail("oat_rip_sample_score: x is required to sample");
@@ -729,6 +734,7 @@ int oat_rip_aggregate(const float* q, int32_t E, int32_t B, int32_t K, int32_t a
                       float* plan, void* stream) {
   if (B <= 0) return 0;
   if (!q || !kstar) return fail("oat_rip_aggregate: null argument");
+  if (g_profile_on) profile_mark("(host gap before call)", (cudaStream_t)stream);
   if (plan && !y) return fail("oat_rip_aggregate: plan requested without y");
   return launch_aggregate(q, E, B, K, algo, y, T, s, kstar, sbest, plan, (cudaStream_t)stream);
 }

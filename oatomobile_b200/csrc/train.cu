@@ -203,6 +203,7 @@ int oat_trainer_destroy(OatTrainer* trainer) {
 int oat_train_forward_backward(OatTrainer* trainer, const float* visual, const float* scalars,
                                const float* target, const float* dropout_mask, int32_t B,
                                int32_t T, float* loss, float* z, float* pred, void* stream) {
+  if (g_profile_on) profile_mark("(host gap before call)", (cudaStream_t)stream);
   if (!trainer || !visual || !scalars || !target || !loss)
     return fail("oat_train_forward_backward: null argument");
   if (B <= 0 || T <= 0) return fail("oat_train_forward_backward: empty batch");

@@ -43,7 +43,7 @@ def test_mlp_forward_alone():
   """mlp.py:25-72 — merger-shaped and head-shaped stacks against torch on the CPU."""
   from oatomobile_b200.networks import MLP
   torch.manual_seed(3)
-  for sizes, final in (((133, [64, 64, 64]), True), ((64, [32, 4]), False), ((7, [5]), False),
+  for sizes, final in (((133, [64, 64, 64]), True), ((64, [32, 4]), False), ((7, [5, 3]), False),
                        ((300, [1000, 17, 260]), True)):
     mlp = MLP(input_size=sizes[0], output_sizes=sizes[1], activate_final=final)
     x = torch.randn(9, sizes[0])
