@@ -383,6 +383,8 @@ def rip_family_work(cfg, e_local, scenes, rows_sample, rows_score, fusion):
   f = lambda pred: sum(layer_flops(l) for l in L if pred(l))
   fused_expand = {"features.2", "features.3", "features.4"} if fusion & 0b1110 else set()
   fused_f1 = bool(fusion & 16)
+  # bit 5: expand + depthwise of features.5-17 inside the tcgen05 GEMM (depthwise epilogue)
+  late = {"features.%d" % i for i in range(5, 18)} if fusion & 32 else set()
   fam = {}
   fam["transform"] = (0.0, scenes * C * (200 * 200 + 100 * 100) * 4.0, "hbm")
   fam["stem"] = (img * f(lambda l: l[0] == "stem"),
@@ -393,12 +395,16 @@ def rip_family_work(cfg, e_local, scenes, rows_sample, rows_score, fusion):
                             img * sum(2500 * 16 + 625 * 96 if n == "features.2" else
                                       625 * 24 + 625 * 144 if n == "features.3" else
                                       625 * 24 + 169 * 144 for n in fused_expand) * 4.0, "hbm")
-  fam["fused_block"] = (0.0, 0.0, "tensor")  # filled by encoder_fused_work() when that path runs
+  # block input (expand: pixels x K) + depthwise output (pixels_out x channels)
+  fam["tc_expand_dw"] = (img * f(lambda l: l[1] in late and l[0] in ("expand", "dw")),
+                         img * sum(l[2] * (l[3] if l[0] == "expand" else l[4]) for l in L
+                                   if l[1] in late and l[0] in ("expand", "dw")) * 4.0, "tensor")
   pw = lambda l: (l[0] in ("expand", "project", "last", "fc") and
-                  not (l[0] == "expand" and l[1] in fused_expand) and
+                  not (l[0] == "expand" and (l[1] in fused_expand or l[1] in late)) and
                   not (l[0] == "project" and l[1] == "features.1" and fused_f1))
   fam["tc_pw_gemm"] = (img * f(pw), img * sum((l[3] + l[4]) * l[2] for l in L if pw(l)) * 4.0, "tensor")
-  dwl = lambda l: l[0] == "dw" and l[1] not in fused_expand and not (l[1] == "features.1" and fused_f1)
+  dwl = lambda l: (l[0] == "dw" and l[1] not in fused_expand and l[1] not in late and
+                   not (l[1] == "features.1" and fused_f1))
   fam["depthwise"] = (img * f(dwl), img * sum(2.0 * l[2] * l[4] for l in L if dwl(l)) * 4.0, "hbm")
   fam["pool"] = (0.0, img * (16 + 1) * 1280 * 4.0, "hbm")
   fam["merger"] = (img * 2.0 * (133 * 64 + 64 * 64 + 64 * 64), img * (133 + 64) * 4.0, "hbm")

@@ -83,8 +83,12 @@ OAT_API int oat_ensemble_set_pw_impl(OatEnsemble* ens, int32_t impl);
  * features.0 + features.1 (stem, depthwise, project) in one kernel; bits 1..3 = expand 1x1 +
  * depthwise 3x3 of features.2 / .3 / .4 in one kernel, the 6x expanded tensor staying in
  * shared memory; bit 4 = depthwise 3x3 + project of features.1 in one kernel (ignored when
- * bit 0 is set).  Plain FP32 FMA arithmetic; results agree with the unfused path to
- * rounding.  Default: 30 (OAT_FUSE_DEFAULT), or the environment variable OAT_FUSE.   */
+ * bit 0 is set); bit 5 = expand 1x1 + depthwise 3x3 of features.5-17 inside the tcgen05 GEMM
+ * (the depthwise window slides over the slab its epilogue stages in shared memory; needs the
+ * tcgen05 pointwise family; correct but measured SLOWER than the separate launches on B200 —
+ * the depthwise arithmetic lands on the GEMM's eight epilogue warps — so it is opt-in).
+ * Results agree with the unfused path to rounding.
+ * Default: 30 (OAT_FUSE_DEFAULT), or the environment variable OAT_FUSE.               */
 OAT_API int oat_ensemble_set_fusion(OatEnsemble* ens, int32_t mask);
 OAT_API int oat_ensemble_get_fusion(const OatEnsemble* ens);
 /* Kernel family of the fused expand+depthwise blocks when the pointwise family is tcgen05:

@@ -144,8 +144,8 @@ def set_default_fusion(mask) -> None:
   """Fusion mask (see `oat_ensemble_set_fusion`) for ensembles created from now on;
   None restores the library default."""
   global _default_fusion
-  if mask is not None and not 0 <= int(mask) <= 31:
-    raise ValueError("fusion mask must be in [0, 31]")
+  if mask is not None and not 0 <= int(mask) <= 63:
+    raise ValueError("fusion mask must be in [0, 63]")
   _default_fusion = None if mask is None else int(mask)
 
 
@@ -246,7 +246,8 @@ class EnsembleHandle:
 
   def set_fusion(self, mask: int) -> None:
     """Bit 0: features.0+1 as one kernel; bits 1-3: expand+depthwise of features.2-4 fused;
-    bit 4: depthwise+project of features.1 fused."""
+    bit 4: depthwise+project of features.1 fused; bit 5: expand+depthwise of features.5-17 inside
+    the tcgen05 GEMM (depthwise epilogue)."""
     check(lib().oat_ensemble_set_fusion(self.ptr, int(mask)))
 
   def fusion(self) -> int:

@@ -425,7 +425,7 @@ int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble
 #define OAT_FUSE_DEFAULT 30
 #endif
   e->fuse = OAT_FUSE_DEFAULT;
-  if (const char* env = getenv("OAT_FUSE")) e->fuse = atoi(env) & 31;
+  if (const char* env = getenv("OAT_FUSE")) e->fuse = atoi(env) & 63;
   if (const char* env = getenv("OAT_FUSE_TC")) e->fuse_tc = atoi(env) < 0 ? 0 : (atoi(env) > 2 ? 2 : atoi(env));
   // ---- tensor-core copies of every pointwise layer: [E][N][K], TF32 hi/lo split ----
   {
@@ -439,7 +439,7 @@ int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble
     layers.push_back({320, 1280});
     layers.push_back({1280, OAT_ENC_FEATURES});
     size_t total = 0;
-    for (const L& l : layers) total += (size_t)num_models * (2 * (size_t)l.K * l.N + l.N);
+    for (const L& l : layers) total += (size_t)num_models * (3 * (size_t)l.K * l.N + l.N);
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(e->device);
@@ -457,6 +457,7 @@ int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble
       const size_t kn = (size_t)t.K * t.N;
       t.wh = p; p += kn * num_models;
       t.wl = p; p += kn * num_models;
+      t.wr = p; p += kn * num_models;
       t.bias = p; p += (size_t)t.N * num_models;
       for (int mi = 0; mi < num_models && rc == 0; ++mi) {
         const OatModel* m = models[mi];
@@ -470,7 +471,7 @@ int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble
           if (cw) break;
         }
         if (!cw) cw = (li == layers.size() - 2) ? &m->last : &m->fc;
-        rc = tc_pack_weights(cw->w, t.K, t.N, t.wh + kn * mi, t.wl + kn * mi, 0);
+        rc = tc_pack_weights(cw->w, t.K, t.N, t.wh + kn * mi, t.wl + kn * mi, t.wr + kn * mi, 0);
         if (rc == 0 && cudaMemcpy(t.bias + (size_t)t.N * mi, cw->b, t.N * sizeof(float),
                                   cudaMemcpyDeviceToDevice) != cudaSuccess)
           rc = fail("oat_ensemble_create: bias copy failed");
@@ -498,7 +499,7 @@ int oat_ensemble_set_pw_impl(OatEnsemble* ens, int32_t impl) {
 
 int oat_ensemble_set_fusion(OatEnsemble* ens, int32_t mask) {
   if (!ens) return fail("oat_ensemble_set_fusion: null ensemble");
-  if (mask < 0 || mask > 31) return fail("oat_ensemble_set_fusion: mask must be in [0, 31]");
+  if (mask < 0 || mask > 63) return fail("oat_ensemble_set_fusion: mask must be in [0, 63]");
   ens->fuse = mask;
   return 0;
 }

@@ -104,6 +104,7 @@ namespace oat {
 struct TcLayer {  // one pointwise layer of the whole ensemble, tensor-core layout
   float* wh = nullptr;    // [E][N][K] TF32-exact high parts
   float* wl = nullptr;    // [E][N][K] low parts
+  float* wr = nullptr;    // [E][N][K] unsplit folded weights (split in shared memory by the GEMM)
   float* bias = nullptr;  // [E][N]
   int K = 0, N = 0;
 };

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const __grid_constant__ Pw
 int launch_pw(const PwArgs& a, int E, cudaStream_t stream, const TcLayer* tc = nullptr) {
   if (tc != nullptr) {  // tcgen05 / TMA path (3xTF32)
     TcGemmProblem p;
-    p.A = a.A; p.Wh = tc->wh; p.Wl = tc->wl; p.bias = tc->bias; p.R = a.R; p.C = a.C;
+    p.A = a.A; p.Wh = tc->wh; p.Wl = tc->wl; p.Wr = tc->wr; p.bias = tc->bias; p.R = a.R; p.C = a.C;
     p.M = a.M; p.K = a.K; p.N = a.N; p.E = E; p.relu6 = a.relu6;
     return tc_pw_gemm(p, stream);
   }
@@ -657,6 +657,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       if (int rc = prefix_done(1, x, blk.hout, blk.cout)) return rc < 0 ? 0 : rc;
       continue;
     }
+    bool dw_fused = false;
     const bool fuse_block = bi >= 1 && bi <= 3 && ((ens->fuse >> bi) & 1) &&
                             fused_block_supported(blk.cin, blk.hid, blk.stride, blk.hin);
     if (fuse_block) {  // expand + depthwise in one kernel: the 6x tensor stays in shared memory
@@ -670,6 +671,23 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       f.tensor_cores = ens->pw_impl == 1 ? ens->fuse_tc : 0;
       if (int rc = launch_fused_expand_dw(f, stream)) return rc;
       ++li;  // the expand layer's tensor-core copy is not used
+    } else if (blk.hid != blk.cin && (ens->fuse & 32) && ens->pw_impl == 1 &&
+               tc_dw_epilogue_supported(blk.hin, blk.stride, blk.hid)) {
+      // expand 1x1 + depthwise 3x3 in ONE tensor-core kernel (features.5-17): the M tiles hold whole
+      // images, so the depthwise window slides over the slab the GEMM epilogue has just staged in
+      // shared memory (tc_gemm.cu); the 6x expanded tensor is never written
+      const TcLayer* t = &ens->tc[li];
+      ++li;
+      TcGemmProblem p;
+      p.A = x; p.Wh = t->wh; p.Wl = t->wl; p.Wr = t->wr; p.bias = t->bias; p.R = nullptr; p.C = nullptr;
+      p.M = Min; p.K = blk.cin; p.N = blk.hid; p.E = E; p.relu6 = 1;
+      p.dw_out = ens->bufH2; p.B = B; p.hin = blk.hin; p.hout = blk.hout; p.stride = blk.stride;
+      for (int e = 0; e < E; ++e) {
+        p.dw_w[e] = ens->models[e]->blocks[bi].dw.w;
+        p.dw_b[e] = ens->models[e]->blocks[bi].dw.b;
+      }
+      if (int rc = tc_pw_gemm(p, stream)) return rc;
+      dw_fused = true;
     } else if (blk.hid != blk.cin) {  // expand 1x1 + BN + ReLU6
       PwArgs a;
       a.w = table([bi](const OatModel* m) { return m->blocks[bi].expand.w; });
@@ -680,7 +698,7 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
       if (int rc = launch_pw(a, E, stream, tc())) return rc;
       dw_in = ens->bufH1;
     }
-    if (!fuse_block) {  // depthwise 3x3 + BN + ReLU6
+    if (!fuse_block && !dw_fused) {  // depthwise 3x3 + BN + ReLU6
       PtrTable w = table([bi](const OatModel* m) { return m->blocks[bi].dw.w; });
       PtrTable b = table([bi](const OatModel* m) { return m->blocks[bi].dw.b; });
       const int64_t total = (int64_t)B * blk.hout * (blk.hid / 4);

@@ -103,6 +103,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// One lane of a converged warp (elect.sync): behind `if (lane == 0)` ptxas wraps every tcgen05
+// instruction (uniform-datapath operands) in an ELECT / BRA.U.ANY serialisation loop — measured in
+// the GEMM (tools/tc_trace.py) at ~80 cycles per MMA, which is what the N = 32 head MMAs cost.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "     elect.sync %%rx|%%px, %2;\n"
+      "@%%px mov.s32 %1, 1;\n"
+      "     mov.s32 %0, %%rx;\n"
+      "}\n"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFF));
+  return pred;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -223,34 +240,41 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc2_kernel(const __grid_cons
 
   if (warp == 16) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the event loop (uniform control flow); one elected lane issues.
+    {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // weight image -> async proxy
       const uint32_t idesc_hh = (1u << 4) | (2u << 7) | (2u << 10) | ((192u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc_hd = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      // issues the 24 MMAs of one GEMM and commits them to `bar` (and to `bar2` if non-zero)
       auto issue = [&](uint32_t d_tmem, uint32_t w_hi, uint32_t w_lo, uint32_t w_kb_bytes,
-                       uint32_t idesc) {
-        // corrections first (accumulator still ~2^-11 of its final size), main product last
-        uint32_t acc = 0;
+                       uint32_t idesc, uint32_t bar, uint32_t bar2) {
+        if (elect_one_sync()) {
+          // corrections first (accumulator still ~2^-11 of its final size), main product last
+          uint32_t acc = 0;
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t dHh = make_desc_sw128(sbase + OFF_HHI + kb * kH_BYTES);
-          const uint64_t dHl = make_desc_sw128(sbase + OFF_HLO + kb * kH_BYTES);
-          const uint64_t dWh = make_desc_sw128(w_hi + kb * w_kb_bytes);
-          const uint64_t dWl = make_desc_sw128(w_lo + kb * w_kb_bytes);
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t dHh = make_desc_sw128(sbase + OFF_HHI + kb * kH_BYTES);
+            const uint64_t dHl = make_desc_sw128(sbase + OFF_HLO + kb * kH_BYTES);
+            const uint64_t dWh = make_desc_sw128(w_hi + kb * w_kb_bytes);
+            const uint64_t dWl = make_desc_sw128(w_lo + kb * w_kb_bytes);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            umma_tf32(d_tmem, dHl + 2 * ks, dWh + 2 * ks, idesc, acc);
-            acc = 1;
-            umma_tf32(d_tmem, dHh + 2 * ks, dWl + 2 * ks, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_tf32(d_tmem, dHl + 2 * ks, dWh + 2 * ks, idesc, acc);
+              acc = 1;
+              umma_tf32(d_tmem, dHh + 2 * ks, dWl + 2 * ks, idesc, 1u);
+            }
           }
-        }
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t dHh = make_desc_sw128(sbase + OFF_HHI + kb * kH_BYTES);
-          const uint64_t dWh = make_desc_sw128(w_hi + kb * w_kb_bytes);
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t dHh = make_desc_sw128(sbase + OFF_HHI + kb * kH_BYTES);
+            const uint64_t dWh = make_desc_sw128(w_hi + kb * w_kb_bytes);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, dHh + 2 * ks, dWh + 2 * ks, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, dHh + 2 * ks, dWh + 2 * ks, idesc, 1u);
+          }
+          umma_commit(bar);
+          if (bar2) umma_commit(bar2);
         }
+        __syncwarp();
       };
       // Per tile: event 0 = h_0 published -> recurrent GEMM of step 0; event t+1 = h_t
       // published -> head GEMM of step t, then the recurrent GEMM of step t+1.  After the
@@ -260,22 +284,21 @@ __global__ void __launch_bounds__(TTHREADS, 1) flow_tc2_kernel(const __grid_cons
 #pragma unroll
         for (int tl = 0; tl < 2; ++tl) {
           if (ev[tl] > T) continue;
-          if (!mbar_try_wait(bar_h_of(tl), (uint32_t)(ev[tl] & 1))) continue;
+          // uniform decision: every lane must have seen the phase complete
+          if (!__all_sync(0xffffffffu, mbar_try_wait(bar_h_of(tl), (uint32_t)(ev[tl] & 1)))) continue;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d0 = tmem + (uint32_t)(tl * 256);
           if (ev[tl] == 0) {
-            issue(d0, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh);
-            umma_commit(bar_d_of(tl));
+            issue(d0, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh, bar_d_of(tl), bar_w_of(tl));
           } else {
             const int t = ev[tl] - 1;
-            issue(d0 + 192, sbase + OFF_W1HI, sbase + OFF_W1LO, kW1_BYTES, idesc_hd);
-            umma_commit(bar_d2_of(tl));
             if (t + 1 < T) {
-              issue(d0, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh);
-              umma_commit(bar_d_of(tl));
+              issue(d0 + 192, sbase + OFF_W1HI, sbase + OFF_W1LO, kW1_BYTES, idesc_hd, bar_d2_of(tl), 0u);
+              issue(d0, sbase + OFF_WHI, sbase + OFF_WLO, kW_BYTES, idesc_hh, bar_d_of(tl), bar_w_of(tl));
+            } else {
+              issue(d0 + 192, sbase + OFF_W1HI, sbase + OFF_W1LO, kW1_BYTES, idesc_hd, bar_d2_of(tl), bar_w_of(tl));
             }
           }
-          umma_commit(bar_w_of(tl));
           ++ev[tl];
         }
       }

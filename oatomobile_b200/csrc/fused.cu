@@ -54,6 +54,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// One lane of a converged warp (elect.sync); see tc_gemm.cu: behind `if (threadIdx.x == 0)` every
+// tcgen05.mma is wrapped in an ELECT / BRA.U.ANY serialisation loop by ptxas.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "     elect.sync %%rx|%%px, %2;\n"
+      "@%%px mov.s32 %1, 1;\n"
+      "     mov.s32 %0, %%rx;\n"
+      "}\n"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFF));
+  return pred;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -154,7 +170,7 @@ struct PipeExec {
   __device__ __forceinline__ void mma(int buf, int acc, int N, const float* a_tile, const float* b_tile, int K) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes -> tensor core
     p_barrier();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32 && elect_one_sync()) {  // warp 0 arrives converged from the barrier
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
                              ((uint32_t)(fused::kTileRows >> 4) << 24);

@@ -14,12 +14,12 @@ from tests.emu import fused_driver as FD
 PFX = "_encoder._model.features."
 
 
-def _prefix_activations(sd, visual):
-  """Oracle activations: stem out, block-1 out, then for blocks 2..4 (input, dw output, output)."""
+def _prefix_activations(sd, visual, blocks=4):
+  """Oracle activations: stem out, block-1 out, then for blocks 2..`blocks` (dw output, output)."""
   with torch.no_grad():
     x = R._conv_bn_relu6(visual, sd, PFX + "0", stride=2, groups=1)
     acts = {"stem": x}
-    for idx, cin, hid, cout, stride, res in R.mbv2_block_table()[:4]:
+    for idx, cin, hid, cout, stride, res in R.mbv2_block_table()[:blocks]:
       p = PFX + "%d.conv" % idx
       h = x
       if hid != cin:

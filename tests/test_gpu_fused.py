@@ -51,6 +51,44 @@ def test_prefix_activations_match_oracle(C, B, E, mask, pw):
       assert_close(got[m], want, 2e-5, "mask %d block %d model %d" % (mask, blocks, m))
 
 
+@pytest.mark.parametrize("C,B,E", [(4, 3, 2), (2, 1, 1), (4, 9, 3), (2, 16, 1)])
+@pytest.mark.parametrize("mask", [32, 62])
+def test_expand_dw_epilogue_fusion_matches_oracle(C, B, E, mask):
+  """Bit 5: expand 1x1 + depthwise 3x3 of features.5-17 in one tcgen05 kernel (tc_gemm.cu, the
+  depthwise window slides over the slab staged by the GEMM epilogue).  Every block output from
+  features.5 on against the oracle's layer-by-layer network: 13x13 halves (stride 1 and 2),
+  7x7 pairs of images (odd image counts leave a half-filled tile), 4x4 groups of eight."""
+  from oatomobile_b200 import ops
+  sds = [synthetic_state_dict("dim", C, 140 + m) for m in range(E)]
+  inp = synthetic_inputs(B, C, 1, 4, seed=121)
+  visual = R.transform_visual(inp["lidar"])
+  ens, keep = _ensemble(sds, C, mask)
+  ens_u, keep_u = _ensemble(sds, C, mask & 31)
+  ref = [_prefix_activations(sd, visual, blocks=17) for sd in sds]
+  vis = visual.to(DEV)
+  for blocks in (5, 6, 7, 8, 11, 12, 14, 15, 17):
+    got = ops.encoder_prefix(ens, vis, blocks).cpu()
+    assert not torch.isnan(got).any(), (mask, blocks)
+    # against the same network with separate expand / depthwise launches: rounding only
+    assert_close(got, ops.encoder_prefix(ens_u, vis, blocks).cpu(), 2e-5,
+                 "dw-epilogue vs separate launches, block %d" % blocks)
+    for m in range(E):
+      # raw activations deep in the network carry more element-wise rounding noise than z (which
+      # averages over pixels): the north-star bar (1e-4) is held on z below, 3e-4 here
+      want = ref[m]["out%d" % blocks].permute(0, 2, 3, 1)
+      assert_close(got[m], want, 3e-4, "dw-epilogue mask %d block %d" % (mask, blocks))
+  scalars = torch.cat([inp["velocity"], inp["is_at_traffic_light"], inp["traffic_light_state"]], 1)
+  z = ops.encode(ens, vis, scalars.to(DEV)).cpu()
+  ens0, keep0 = _ensemble(sds, C, mask & 31)
+  z0 = ops.encode(ens0, vis, scalars.to(DEV)).cpu()
+  assert_close(z, z0, 5e-5, "dw-epilogue z vs the unfused late blocks")
+  with torch.no_grad():
+    for m in range(E):
+      want = R.imitative_params(sds[m], visual, inp["velocity"], inp["is_at_traffic_light"],
+                                inp["traffic_light_state"])
+      assert_close(z[m], want, REL_TOL, "dw-epilogue z vs oracle")
+
+
 @pytest.mark.parametrize("pw", ["tcgen05", "tcgen05-all", "simt"])
 def test_fused_z_matches_unfused_and_oracle(pw):
   from oatomobile_b200 import ops

@@ -21,7 +21,7 @@ def kernel_family(request):
   flow = request.param if request.param in ("tcgen05", "simt", "tcgen05x2") else "tcgen05x2"
   _native.set_flow_impl(flow)
   _native.set_default_pw_impl("simt" if request.param == "simt" else "tcgen05")
-  _native.set_default_fusion({"unfused": 0, "fused-all": 15}.get(request.param))  # None: default (30)
+  _native.set_default_fusion({"unfused": 0, "fused-all": 47}.get(request.param))  # None: default (30)
   yield request.param
   _native.set_flow_impl("tcgen05x2")  # library default
   _native.set_default_pw_impl("tcgen05")
