@@ -324,6 +324,25 @@ def train_metric(tcfg):
       tcfg["kind"].upper(), tcfg["T"])
 
 
+def pin_to_gpu_numa_node(index):
+  """Multi-rank runs: bind this process to the CPU cores NVML reports as local to its GPU before
+  any pinned host buffer is allocated, so the e2e arm's H2D source pages live on the GPU's own
+  NUMA node instead of all ranks pulling from one node.  Returns the number of cores, or None."""
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(index)
+    words = (os.cpu_count() + 63) // 64
+    mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+    cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+    allowed = os.sched_getaffinity(0)
+    cpus = (cpus & allowed) or allowed
+    os.sched_setaffinity(0, cpus)
+    return len(cpus)
+  except Exception:
+    return None
+
+
 # ----------------------------------------------------------------------------------
 # GPU arm: RIP sample-and-score
 # ----------------------------------------------------------------------------------
@@ -340,6 +359,7 @@ class Dist:
       raise SystemExit("launch N>1 with torchrun (one rank per GPU)")
     torch.cuda.set_device(self.local_rank)
     self.dev = torch.device("cuda", self.local_rank)
+    self.numa = pin_to_gpu_numa_node(self.local_rank) if self.world > 1 else None
     if self.world > 1:
       dist.init_process_group("nccl", device_id=self.dev)
     self.dist = dist
@@ -670,6 +690,8 @@ def rip_line(D, r, args, peaks, warmup):
                             "pass); flops counted = E passes",
           "launch": ("encoder stage replayed as one CUDA graph per input-buffer set"
                      if not args.no_cuda_graphs else "one launch per kernel"),
+          "host_numa": ("each rank bound to the %s cores NVML lists as local to its GPU" % D.numa
+                        if D.numa else "no binding"),
       },
       "stages_ms": r["stages"], "clocks": r["clocks"], "gpu_launches": r["launches"],
   }

@@ -70,6 +70,12 @@ static_assert((TC_BM * TC_BK / 4) % TC_SPLIT_THREADS == 0, "splitters must tile 
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_MAX_STAGES = 5;
 constexpr int TC_TMEM_COLS = 512;
+#ifndef OAT_TC_BN_SHALLOW_DEFAULT
+#define OAT_TC_BN_SHALLOW_DEFAULT 128
+#endif
+#ifndef OAT_TC_STACK_K_DEFAULT
+#define OAT_TC_STACK_K_DEFAULT 1000000   // stacked two-MMA form: measured no faster than three MMAs (off)
+#endif
 #ifndef OAT_TC_TS_DEFAULT
 #define OAT_TC_TS_DEFAULT 0
 #endif
@@ -108,7 +114,11 @@ struct TcArgs {
                // from shared memory.  Measured (tools/tc_trace.py): the SS form is bound by shared-
                // memory bandwidth (TMA writes + split reads/writes + 2 x 4 KB of A per K slice)
   int a_ring;  // ts: number of A slots (64 TMEM columns each: a_hi | a_lo) behind the accumulators
+  int acc_cols_per_buf;  // TMEM columns of one accumulator group
   int acc_cols;  // ts: TMEM columns taken by the accumulators (the A ring starts there)
+  int stack;   // 1 (deep K): 3xTF32 in two MMAs, a_hi x [W_hi ; W_lo] (N = 2*BN) + a_lo x W_hi, accumulators
+               //   C x [hi*hi | hi*lo] + [lo*hi];  0 (shallow K, epilogue-bound layers): three MMAs of width
+               //   BN into C x [hi*hi] + [lo*hi + hi*lo] — one accumulator less for the epilogue to read
   int wsplit;  // 1: mapWh addresses the UNSPLIT weights; the splitter warps form W_hi / W_lo in smem
   int direct;  // 1: the epilogue stores straight from registers (no smem staging, no TMA store):
                // frees 64 KB for a third pipeline stage on the stage-starved late layers
@@ -259,29 +269,48 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
 // (one MMA with the stacked B operand [W_hi ; W_lo] writes both halves), then a_lo*w_hi (BN columns).
 // Returns in v the 16 columns c..c+15 of  sum_j main_j  +  (sum_j hilo_j + lohi),  main chunks
 // added in round-to-nearest fp32 first (see the header on the accumulate truncation).
-__device__ __forceinline__ void acc_load16(uint32_t taddr, int c, int C, int BN, int used, float (&v)[16]) {
+__device__ __forceinline__ void acc_load16(uint32_t taddr, int c, int C, int BN, int used, int stack,
+                                           float (&v)[16]) {
   float u[16];
-  {
-    uint32_t r0[16], r1[16], r2[16];
-    tmem_ld16_nowait(taddr + (uint32_t)c, r0);
-    tmem_ld16_nowait(taddr + (uint32_t)(BN + c), r1);
-    tmem_ld16_nowait(taddr + (uint32_t)(2 * C * BN + c), r2);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (stack) {
+    {
+      uint32_t r0[16], r1[16], r2[16];
+      tmem_ld16_nowait(taddr + (uint32_t)c, r0);
+      tmem_ld16_nowait(taddr + (uint32_t)(BN + c), r1);
+      tmem_ld16_nowait(taddr + (uint32_t)(2 * C * BN + c), r2);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      v[i] = __uint_as_float(r0[i]);
-      u[i] = __uint_as_float(r1[i]) + __uint_as_float(r2[i]);
+      for (int i = 0; i < 16; ++i) {
+        v[i] = __uint_as_float(r0[i]);
+        u[i] = __uint_as_float(r1[i]) + __uint_as_float(r2[i]);
+      }
     }
-  }
-  for (int j = 1; j < used; ++j) {
-    uint32_t r0[16], r1[16];
-    tmem_ld16_nowait(taddr + (uint32_t)(2 * j * BN + c), r0);
-    tmem_ld16_nowait(taddr + (uint32_t)(2 * j * BN + BN + c), r1);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int j = 1; j < used; ++j) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16_nowait(taddr + (uint32_t)(2 * j * BN + c), r0);
+      tmem_ld16_nowait(taddr + (uint32_t)(2 * j * BN + BN + c), r1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      v[i] += __uint_as_float(r0[i]);
-      u[i] += __uint_as_float(r1[i]);
+      for (int i = 0; i < 16; ++i) {
+        v[i] += __uint_as_float(r0[i]);
+        u[i] += __uint_as_float(r1[i]);
+      }
+    }
+  } else {  // C x [hi*hi] then one correction tile
+    {
+      uint32_t r0[16], r1[16];
+      tmem_ld16_nowait(taddr + (uint32_t)c, r0);
+      tmem_ld16_nowait(taddr + (uint32_t)(C * BN + c), r1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r0[i]); u[i] = __uint_as_float(r1[i]); }
+    }
+    for (int j = 1; j < used; ++j) {
+      uint32_t r0[16];
+      tmem_ld16_nowait(taddr + (uint32_t)(j * BN + c), r0);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r0[i]);
     }
   }
 #pragma unroll
@@ -443,8 +472,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
         const uint32_t aph = (a.nbuf == 2) ? ((lt >> 1) & 1) : (lt & 1);
         mbar_wait(bar_tempty(ab), aph ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t grp = tmem_base + (uint32_t)(ab * (2 * C + 1) * BN);
-        const uint32_t d_lohi = grp + (uint32_t)(2 * C * BN);
+        const uint32_t grp = tmem_base + (uint32_t)(ab * a.acc_cols_per_buf);
+        const uint32_t d_lohi = grp + (uint32_t)((a.stack ? 2 * C : C) * BN);  // stack 0: lo*hi + hi*lo
         int kc = 0;  // kb % C
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = ring_s;
@@ -461,7 +490,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
           const uint64_t dWh = make_desc_sw128(a.wres ? rWh(kb) : sWh(s));
           const int kleft = a.K - kb * TC_BK;
           const int slices = kleft >= TC_BK ? 4 : (kleft + 7) / 8;  // zero-filled k-slices skipped
-          const uint32_t d_hi = grp + (uint32_t)(kcc * 2 * BN);  // [a_hi*w_hi | a_hi*w_lo]
+          const uint32_t d_hi = grp + (uint32_t)(kcc * (a.stack ? 2 : 1) * BN);  // [a_hi*w_hi (| a_hi*w_lo)]
+          const uint64_t dWl = make_desc_sw128(sWl(s));
           if (a.ts) {
             const uint32_t ta_hi = tmem_base + (uint32_t)(a.acc_cols + ja * 64), ta_lo = ta_hi + 32u;
             if (elect_one_sync()) {
@@ -475,6 +505,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
               }
               umma_commit(bar_empty(s));   // W tiles (and the raw A tile) of the stage are free
               umma_commit(bar_afree(ja));  // the A slot in tensor memory may be overwritten
+            }
+          } else if (!a.stack) {
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks < slices) {
+                  const uint64_t off = (uint64_t)(ks * 2);
+                  umma_tf32(d_lohi, dAl + off, dWh + off, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+                  umma_tf32(d_lohi, dAh + off, dWl + off, idesc, 1u);
+                  umma_tf32(d_hi, dAh + off, dWh + off, idesc, (kb < C && ks == 0) ? 0u : 1u);
+                }
+              }
+              umma_commit(bar_empty(s));
             }
           } else if (elect_one_sync()) {
 #pragma unroll
@@ -646,7 +689,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
         const int opi = (oy1 - oy0) * hout;                   // output pixels per image in this tile
         const int P = nim * opi;
         const int rrow_i = qd * 32 + lane;                    // row inside the tile = TMEM lane
-        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * (2 * C + 1) * BN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * a.acc_cols_per_buf);
         const float* __restrict__ bias = a.bias + (int64_t)e * a.N;
         const int c4 = et & 7;                                // float4 column of this thread in a slab
         const int64_t out_base = ((int64_t)e * a.Mout + (int64_t)img0 * hout * hout + (int64_t)oy0 * hout) * a.N;
@@ -664,7 +707,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 4; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(bias + n + 4 * j));
             float v[16];
-            acc_load16(taddr, c, C, BN, used, v);
+            acc_load16(taddr, c, C, BN, used, a.stack, v);
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               const float4 b = bq[j >> 2];
@@ -722,7 +765,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
       const int rrow_i = qd * 32 + lane;           // row inside the tile = TMEM lane
       const int row = m0 + rrow_i;
       const bool row_ok = row < a.M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * (2 * C + 1) * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ab * a.acc_cols_per_buf);
       const float* __restrict__ bias = a.bias + (int64_t)e * a.N;
       const float* __restrict__ rrow = (a.R && row_ok) ? a.R + ((int64_t)e * a.M + row) * a.N : nullptr;
       if (a.direct) {
@@ -737,7 +780,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
             bq[j] = (n + 4 * j < a.N) ? __ldg(reinterpret_cast<const float4*>(bias + n + 4 * j))
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
           float v[16];
-            acc_load16(taddr, c, C, BN, used, v);
+            acc_load16(taddr, c, C, BN, used, a.stack, v);
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -774,7 +817,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pw_gemm_kernel(const __grid_
             bq[j] = (n + 4 * j < a.N) ? __ldg(reinterpret_cast<const float4*>(bias + n + 4 * j))
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
           float v[16];
-            acc_load16(taddr, c, C, BN, used, v);
+            acc_load16(taddr, c, C, BN, used, a.stack, v);
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -929,25 +972,38 @@ int tc_pw_gemm(const TcGemmProblem& p, cudaStream_t stream) {
   // bias of the tensor core's fp32 accumulate, (K/8)*2^-24/C per output, below 4e-6
   a.chunks = (p.K + 511) / 512;
   if (a.chunks > 3) a.chunks = 3;
-  const int sets = 2 * a.chunks + 1;                   // C x [hi*hi | hi*lo] + lo*hi
+  static const int stack_k = []() { const char* e = getenv("OAT_TC_STACK_K"); return e ? atoi(e) : OAT_TC_STACK_K_DEFAULT; }();
   static const int ts_env = []() { const char* e = getenv("OAT_TC_TS"); return e ? atoi(e) : -1; }();
   a.ts = (ts_env >= 0 ? ts_env != 0 : OAT_TC_TS_DEFAULT) ? 1 : 0;
+  a.stack = (p.K >= stack_k || a.ts) ? 1 : 0;  // the tensor-memory A operand is written for the stacked form
+  const int sets = a.stack ? 2 * a.chunks + 1 : a.chunks + 1;
   a.a_ring = 2;
   const int tmem_for_acc = TC_TMEM_COLS - (a.ts ? a.a_ring * 64 : 0);
   int bn_max = ((tmem_for_acc / sets) / 32) * 32;      // (2C+1)*BN (+ A ring) <= 512 TMEM columns
 #ifndef OAT_TC_BN_CAP
 #define OAT_TC_BN_CAP 128                              // the stacked MMA has N = 2*BN <= 256
 #endif
-  if (bn_max > OAT_TC_BN_CAP) bn_max = OAT_TC_BN_CAP;
-  // direct-store epilogue (deep K, see below): 16-column granules, so N = 160 / 320 tile without
-  // waste (2 x 80, 4 x 80); the staged epilogues need whole 32-column slabs
+  if (bn_max > (a.stack ? OAT_TC_BN_CAP : 160)) bn_max = a.stack ? OAT_TC_BN_CAP : 160;
+  // Shallow-K layers (the expand convolutions: 1-5 k-blocks per tile) spend most of a tile in the
+  // epilogue; tiles narrow enough for TWO accumulator groups (2 * 3 * BN <= 512) let the epilogue
+  // of tile i overlap the main loop of tile i+1.  OAT_TC_BN_SHALLOW=<cols> overrides (0: off).
+  static const int shallow_env = []() { const char* e = getenv("OAT_TC_BN_SHALLOW"); return e ? atoi(e) : -1; }();
+  const int shallow = shallow_env >= 0 ? shallow_env : OAT_TC_BN_SHALLOW_DEFAULT;
+  static const int shallow_k = []() { const char* e = getenv("OAT_TC_BN_SHALLOW_K"); return e ? atoi(e) : 160; }();
+  if (shallow > 0 && p.K <= shallow_k && a.chunks == 1 && bn_max > shallow) bn_max = shallow;
+  // direct-store epilogue for the deep-K layers (the project convolutions, K >= 192: few output
+  // bytes per flop): 16-column granules, so N = 160 / 320 tile without waste (2 x 80, 4 x 80), no
+  // staging barriers.  The shallow-K layers (expand convolutions: output-store bound) keep the
+  // swizzled staging + TMA store, which measured 25 % faster there (profiles/r2_gemm_ab.md).
   static const int direct_env = []() { const char* e = getenv("OAT_TC_DIRECT"); return e ? atoi(e) : -1; }();
-  a.direct = (p.dw_out == nullptr && (direct_env >= 0 ? direct_env != 0 : p.K >= 96)) ? 1 : 0;
+  static const int direct_k = []() { const char* e = getenv("OAT_TC_DIRECT_K"); return e ? atoi(e) : 192; }();
+  a.direct = (p.dw_out == nullptr && (direct_env >= 0 ? direct_env != 0 : p.K >= direct_k)) ? 1 : 0;
   const int gran = a.direct ? 16 : 32;
   a.n_tiles = (p.N + bn_max - 1) / bn_max;
   const int per = (p.N + a.n_tiles - 1) / a.n_tiles;
   a.BN = ((per + gran - 1) / gran) * gran;
   a.nbuf = (2 * sets * a.BN <= tmem_for_acc) ? 2 : 1;
+  a.acc_cols_per_buf = sets * a.BN;
   a.acc_cols = a.nbuf * sets * a.BN;
   a.m_tiles = (p.M + TC_BM - 1) / TC_BM;
   a.dw = p.dw_out != nullptr;

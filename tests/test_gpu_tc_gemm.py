@@ -57,3 +57,21 @@ def test_tc_gemm_matches_fp64(E, M, K, N, relu6, residual):
   # 3xTF32 (a_lo*w_lo dropped: 2^-22 per product) + chunked accumulation (tc_gemm.cu):
   # the tensor core's truncating accumulate stays below ~1.5e-6 per layer.
   assert_close(C, ref, 1e-5, "tc gemm E%d M%d K%d N%d" % (E, M, K, N))
+
+
+@pytest.mark.parametrize("env", [{"OAT_TC_TS": "1"}, {"OAT_TC_STACK_K": "0"}, {"OAT_TC_WSPLIT": "1"},
+                                 {"OAT_TC_DIRECT": "1"}, {"OAT_TC_DIRECT": "0", "OAT_TC_BN_SHALLOW": "0"}],
+                         ids=lambda e: ",".join("%s=%s" % kv for kv in sorted(e.items())))
+def test_evaluated_gemm_variants_stay_correct(env):
+  """The GEMM's opt-in forms (tensor-memory A operand, stacked [W_hi;W_lo] two-MMA form, in-SM
+  weight split, direct-store epilogue everywhere / nowhere) are selected by environment variables
+  read once per process: every (K, N) family of this file is re-run against float64 in a
+  subprocess per variant, so the code paths DESIGN.md §12 reports on cannot rot."""
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-k", "not variants", __file__],
+                     env=dict(os.environ, **env), cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                     timeout=600)
+  assert r.returncode == 0, r.stdout.decode()[-2000:]
