@@ -580,8 +580,81 @@ int launch_transform_visual(const float* lidar, int B, int C, int H, int W, floa
   return 0;
 }
 
+#ifndef OAT_ENC_GROUP_DEFAULT
+#define OAT_ENC_GROUP_DEFAULT 0
+#endif
+static int encoder_forward_group(OatEnsemble* ens, const float* visual, const float* scalars, int B,
+                                 float* z, cudaStream_t stream, int stop_after_blocks, float* prefix_out,
+                                 int prefix_e0);
+
+// The ensemble can be walked in groups of `OAT_ENC_GROUP` models (default: all at once), each group
+// on its OWN stream (fork / join with events, capturable into a CUDA graph): every kernel of the
+// network then covers fewer models, so (1) the activations between consecutive kernels shrink
+// towards the L2 and (2) the persistent kernels of one group fill the SMs the other group's
+// kernel leaves idle in its last wave (e.g. the 128 tiles of a 960->160 project on 148 SMs).
+struct GroupStreams {
+  cudaStream_t s[kMaxModels] = {nullptr};
+  cudaEvent_t fork = nullptr, join[kMaxModels] = {nullptr};
+};
+static GroupStreams* group_streams(int device) {
+  static GroupStreams per_device[64];
+  static bool made[64] = {false};
+  if (device < 0 || device >= 64) return nullptr;
+  GroupStreams* g = &per_device[device];
+  if (!made[device]) {
+    if (cudaEventCreateWithFlags(&g->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (int i = 1; i < kMaxModels; ++i) {
+      if (cudaStreamCreateWithFlags(&g->s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&g->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    made[device] = true;
+  }
+  return g;
+}
+
 int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars, int B,
                     float* z, cudaStream_t stream, int stop_after_blocks, float* prefix_out) {
+  const int E = (int)ens->models.size();
+  static const int group_env = []() { const char* e = getenv("OAT_ENC_GROUP"); return e ? atoi(e) : OAT_ENC_GROUP_DEFAULT; }();
+  static const int serial_env = []() { const char* e = getenv("OAT_ENC_GROUP_SERIAL"); return e ? atoi(e) : 0; }();
+  const int G = (group_env > 0 && group_env < E) ? group_env : E;
+  if (G >= E) return encoder_forward_group(ens, visual, scalars, B, z, stream, stop_after_blocks, prefix_out, 0);
+  // concurrent groups need disjoint workspace slices; the profile's event chain needs one stream
+  GroupStreams* gs = (serial_env || g_profile_on) ? nullptr : group_streams(ens->device);
+  if (gs) OAT_CUDA(cudaEventRecord(gs->fork, stream));
+  const size_t kA = 50 * 50 * 32, kH1 = 50 * 50 * 96, kH2 = 25 * 25 * 144;  // per (model, image), see oat_ensemble_reserve
+  int gi = 0;
+  for (int e0 = 0; e0 < E; e0 += G, ++gi) {
+    const int n = E - e0 < G ? E - e0 : G;
+    OatEnsemble sub;  // a view: the group's models, tensor-core weights and workspace slice
+    sub.models.assign(ens->models.begin() + e0, ens->models.begin() + e0 + n);
+    sub.tc = ens->tc;
+    for (TcLayer& t : sub.tc) {
+      const size_t kn = (size_t)t.K * t.N;
+      t.wh += kn * e0; t.wl += kn * e0; t.wr += kn * e0; t.bias += (size_t)t.N * e0;
+    }
+    sub.pw_impl = ens->pw_impl; sub.fuse = ens->fuse; sub.fuse_tc = ens->fuse_tc; sub.device = ens->device;
+    sub.reserved_batch = ens->reserved_batch;
+    const size_t eb = (size_t)e0 * ens->reserved_batch;
+    sub.bufA = ens->bufA + eb * kA; sub.bufB = ens->bufB + eb * kA;
+    sub.bufH1 = ens->bufH1 + eb * kH1; sub.bufH2 = ens->bufH2 + eb * kH2;
+    sub.pooled = ens->pooled + eb * 1280; sub.feat = ens->feat + eb * 128;
+    cudaStream_t gstream = (gs && gi > 0) ? gs->s[gi] : stream;
+    if (gs && gi > 0) OAT_CUDA(cudaStreamWaitEvent(gstream, gs->fork, 0));
+    const int rc = encoder_forward_group(&sub, visual, scalars, B, z ? z + (size_t)e0 * B * kHidden : nullptr,
+                                         gstream, stop_after_blocks, prefix_out, e0);
+    if (rc) return rc;
+    if (gs && gi > 0) {
+      OAT_CUDA(cudaEventRecord(gs->join[gi], gstream));
+      OAT_CUDA(cudaStreamWaitEvent(stream, gs->join[gi], 0));
+    }
+  }
+  return 0;
+}
+
+static int encoder_forward_group(OatEnsemble* ens, const float* visual, const float* scalars, int B,
+                                 float* z, cudaStream_t stream, int stop_after_blocks, float* prefix_out,
+                                 int prefix_e0) {
   const int E = (int)ens->models.size();
   const OatModel* m0 = ens->models[0];
   const int C = m0->in_channels;
@@ -624,7 +697,8 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
   }
   auto prefix_done = [&](size_t blocks_done, const float* act, int h, int c) -> int {
     if (stop_after_blocks < 0 || (size_t)stop_after_blocks != blocks_done) return 0;
-    OAT_CUDA(cudaMemcpyAsync(prefix_out, act, (size_t)E * B * h * h * c * sizeof(float),
+    OAT_CUDA(cudaMemcpyAsync(prefix_out + (size_t)prefix_e0 * B * h * h * c, act,
+                             (size_t)E * B * h * h * c * sizeof(float),
                              cudaMemcpyDeviceToDevice, stream));
     return -1;
   };
@@ -756,7 +830,8 @@ int encoder_forward(OatEnsemble* ens, const float* visual, const float* scalars,
     if (int rc = launch_pw(a, E, stream, tc())) return rc;
   }
   if (stop_after_blocks == 18) {  // `MobileNetV2.forward` alone: the 128 features, no merger
-    OAT_CUDA(cudaMemcpyAsync(prefix_out, ens->feat, (size_t)E * B * 128 * sizeof(float),
+    OAT_CUDA(cudaMemcpyAsync(prefix_out + (size_t)prefix_e0 * B * 128, ens->feat,
+                             (size_t)E * B * 128 * sizeof(float),
                              cudaMemcpyDeviceToDevice, stream));
     return 0;
   }
