@@ -775,7 +775,7 @@ def run_gpu_train(args):
   cls = ob.ImitativeModel if kind == "dim" else ob.BehaviouralModel
   model = cls(output_shape=(T, 2), in_channels=C)
   model.load_state_dict(synthetic_state_dict(kind, C, 400), strict=True)
-  trainer = Trainer(model.to(dev), lr=1e-3, group=group)
+  trainer = Trainer(model.to(dev), lr=1e-3, group=group, use_cuda_graphs=args.train_graphs)
 
   # synthetic episodes in the on-disk sample format (datasets/carla.py:238-325): HWC lidar,
   # 80-frame futures; the documented loop = collate -> model.transform -> train_step
@@ -869,7 +869,9 @@ def run_gpu_train(args):
                    "bev_channels": C,
                    "parallelism": "data parallel x%d, one NCCL all-reduce of the flat 9.7 MB gradient "
                                   "buffer per step" % world if world > 1 else "single GPU",
-                   "l2": "activations of one step (>1 GB at B=64) exceed L2"},
+                   "l2": "activations of one step (>1 GB at B=64) exceed L2",
+                   "launch": "forward+backward replayed as one CUDA graph" if args.train_graphs
+                             else "one launch per kernel"},
         "clocks": clocks, "gpu_launches": int(launches) * world, "loss": float(loss),
         "e2e": {"value": b_total * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
                 "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(h2d) * world,
@@ -902,6 +904,9 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-eager-baseline", action="store_true")
   ap.add_argument("--no-cfg5", action="store_true", help="N=8: skip the extra BASELINE configs[4] measurement")
+  ap.add_argument("--no-train-graphs", dest="train_graphs", action="store_false",
+                  help="training workloads: one launch per kernel instead of replaying forward+backward as one "
+                       "CUDA graph (Trainer(use_cuda_graphs=True))")
   ap.add_argument("--no-cuda-graphs", action="store_true",
                   help="launch the encoder's kernels one by one instead of replaying a CUDA graph")
   ap.add_argument("--e2e-chunks", type=int, default=1,
