@@ -516,17 +516,17 @@ def run_rip(D, cfg, args, steps, warmup, measure_e2e=True, with_profile=True):
     return model.to(dev).eval()
 
   models = [make(m) for m in range(grank * e_local, (grank + 1) * e_local)]
-  proposal = None if grank == 0 else make(0)
+  proposal = None if (grank == 0 or args.flow_sharding == "scenes") else make(0)
   scorer = RIPScorer(models, "WCM", group=group if gsize > 1 else None, proposal_model=proposal,
-                     use_cuda_graphs=not args.no_cuda_graphs)
+                     use_cuda_graphs=not args.no_cuda_graphs, flow_sharding=args.flow_sharding)
 
   inp = synthetic_inputs(scenes, C, K, T, G_GOALS, seed=group_id)
   host = {k: v.pin_memory() for k, v in inp.items()}
   d = {k: v.to(dev) for k, v in inp.items()}
   x, goal = d.pop("x"), d.pop("goal")
 
-  def step():
-    return scorer(x=x, goal=goal, epsilon=1.0, **d)
+  def step():  # the metric's outputs: plan, kstar, sbest for every scene (no proposal/score tensors gathered)
+    return scorer(x=x, goal=goal, epsilon=1.0, gather_details=False, **d)
 
   for _ in range(max(warmup, 3)):
     step()
@@ -623,7 +623,10 @@ def run_rip(D, cfg, args, steps, warmup, measure_e2e=True, with_profile=True):
     fusion = int(scorer._ensemble().fusion())
   except Exception:
     pass
-  if gsize > 1:
+  if gsize > 1 and args.flow_sharding == "scenes" and scenes % gsize == 0:
+    rows_sample = (scenes // gsize) * K          # every rank: the single-GPU flow stage on its scenes
+    rows_score = (E - 1) * (scenes // gsize) * K
+  elif gsize > 1:
     rows_sample = (scenes // gsize if scenes % gsize == 0 else scenes) * K
     rows_score = e_local * scenes * K
   else:
@@ -683,7 +686,12 @@ def rip_line(D, r, args, peaks, warmup):
           "workload": cfg["name"], "ensemble": cfg["E"], "K": cfg["K"], "T": cfg["T"],
           "bev_channels": cfg["C"], "scenes_total": r["total_scenes"],
           "scenes_per_group": r["scenes"],
-          "parallelism": "ensemble sharded %d model(s)/rank x %d replica group(s)" % (r["e_local"], r["n_groups"]),
+          "parallelism": "ensemble sharded %d model(s)/rank x %d replica group(s)%s" % (
+              r["e_local"], r["n_groups"],
+              "" if r["gsize"] == 1 else (
+                  "; flow stage sharded by scenes behind ONE all-gather of the per-model latents z "
+                  "(decoders replicated, 15 k parameters each)" if args.flow_sharding == "scenes" else
+                  "; flow stage sharded by models: z_0 broadcast, proposal all-gather, all-gather of per-model scores")),
           "l2": "inputs larger than L2 (BEV grids %.0f MB + noise %.0f MB per group step)" %
                 (r["scenes"] * cfg["C"] * 200 * 200 * 4 / 1e6, r["scenes"] * cfg["K"] * cfg["T"] * 8 / 1e6),
           "proposal_score": "q[0] is emitted by the sampling pass (bit-identical to a separate scoring "
@@ -907,6 +915,9 @@ def main():
   ap.add_argument("--no-train-graphs", dest="train_graphs", action="store_false",
                   help="training workloads: one launch per kernel instead of replaying forward+backward as one "
                        "CUDA graph (Trainer(use_cuda_graphs=True))")
+  ap.add_argument("--flow-sharding", default="scenes", choices=["scenes", "models"],
+                  help="sharded ensembles: how the flow stage behind the model-sharded encoders is split "
+                       "(oatomobile_b200/rip.py); 'models' = per-model scores all-gathered")
   ap.add_argument("--no-cuda-graphs", action="store_true",
                   help="launch the encoder's kernels one by one instead of replaying a CUDA graph")
   ap.add_argument("--e2e-chunks", type=int, default=1,

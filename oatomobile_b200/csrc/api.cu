@@ -409,7 +409,6 @@ int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble
   OatEnsemble* e = new OatEnsemble();
   for (int i = 0; i < num_models; ++i) {
     if (!models[i]) { delete e; return fail("oat_ensemble_create: null model"); }
-    if (models[i]->kind == OAT_KIND_FLOW) { delete e; return fail("oat_ensemble_create: flow-only model has no encoder"); }
     if (models[i]->device != models[0]->device || models[i]->kind != models[0]->kind ||
         models[i]->in_channels != models[0]->in_channels) {
       delete e;
@@ -418,6 +417,12 @@ int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble
     e->models.push_back(models[i]);
   }
   e->device = models[0]->device;
+  if (models[0]->kind == OAT_KIND_FLOW) {
+    // decoders only (replicas of every model's AutoregressiveFlow on a rank that shards the flow
+    // stage by scenes): usable with oat_rip_sample_score, no encoder arena, no workspace
+    *out = e;
+    return 0;
+  }
   // Default: depthwise+project of features.1 and expand+depthwise of features.2-4 fused
   // (measured 4.47 -> 4.21 ms per encode at B=256, E=4); the fused features.0+1 kernel is
   // correct but not faster than the separate launches, so bit 0 stays off.
@@ -601,6 +606,7 @@ int oat_encode(OatEnsemble* ens, const float* visual, const float* scalars, int3
                void* stream) {
   if (B <= 0) return 0;
   if (!ens || !visual || !scalars || !z) return fail("oat_encode: null argument");
+  if (ens->models[0]->kind == OAT_KIND_FLOW) return fail("oat_encode: a decoder-only ensemble has no encoder");
   if (g_profile_on) profile_mark("(host gap before call)", (cudaStream_t)stream);
   if (int rc = check_device(ens->device, "oat_encode")) return rc;
   if (int rc = oat_ensemble_reserve(ens, B)) return rc;
@@ -611,6 +617,7 @@ int oat_encode_features(OatEnsemble* ens, const float* visual, int32_t B, float*
                         void* stream) {
   if (B <= 0) return 0;
   if (!ens || !visual || !features) return fail("oat_encode_features: null argument");
+  if (ens->models[0]->kind == OAT_KIND_FLOW) return fail("oat_encode_features: a decoder-only ensemble has no encoder");
   if (int rc = check_device(ens->device, "oat_encode_features")) return rc;
   if (int rc = oat_ensemble_reserve(ens, B)) return rc;
   // stop_after_blocks = 18: the whole MobileNetV2 (features + pool + classifier), no merger
@@ -706,7 +713,8 @@ int oat_rip_sample_score(OatEnsemble* ens, int32_t proposal_idx, const float* z,
   if (proposal_idx >= 0 && !x) return fail("oat_rip_sample_score: x is required to sample");
   if (goal && G < 1) return fail("oat_rip_sample_score: G must be >= 1 when goal is given");
   if (epsilon <= 0.0f) return fail("oat_rip_sample_score: epsilon must be positive");
-  if (ens->models[0]->kind != OAT_KIND_DIM) return fail("oat_rip_sample_score: not ImitativeModels");
+  if (ens->models[0]->kind != OAT_KIND_DIM && ens->models[0]->kind != OAT_KIND_FLOW)
+    return fail("oat_rip_sample_score: not ImitativeModels / AutoregressiveFlows");
   if (int rc = check_device(ens->device, "oat_rip_sample_score")) return rc;
   const int64_t N = (int64_t)B * K;
   if (N <= 0) return 0;

@@ -8,7 +8,20 @@ Assembled from the reference's own primitives:
   k*    = argmin_k s ; plan = y[b, k*]
 
 Multi-GPU: the ensemble is sharded in contiguous blocks of
-E/R models per rank.  One tiny broadcast of z_0 lets every rank decode proposals with
+E/R models per rank — the ENCODERS, which hold 99.4 % of a model's parameters and all of the
+stage's cost, never leave their rank.  Two layouts for the flow stage behind them:
+
+`flow_sharding="scenes"` (default): the per-model latents `z` ([E_local,B,64], 64 KB per model)
+are all-gathered — the ONE data-path collective between the stages — and every rank runs the
+single-GPU sample-and-score on its B/R scenes with replicas of all E flow decoders (15 k
+parameters each, copied from their owners at construction): proposals from model 0 (whose
+score comes out of the sampling pass), E-1 scoring passes, aggregation, argmin.  No proposal
+or score tensor crosses NVLink; only the selected plans (B x T x 2 floats) are gathered at the
+end.  Every rank does exactly 1/R of the single-GPU flow work.
+
+`flow_sharding="models"` (the layout BASELINE.json's north_star spells out): each rank scores
+all proposals under ITS models and the per-model scores are all-gathered:
+one tiny broadcast of z_0 lets every rank decode proposals with
 the (replicated, 61 KB) decoder of model 0: each rank decodes 1/R of the scenes and the
 slices are all-gathered over NVLink (rows are independent, so the gathered y is
 bit-identical to a single-GPU decode; when the scene count does not divide, every rank
@@ -34,7 +47,7 @@ class RIPScorer:
 
   def __init__(self, models: Sequence[ImitativeModel], algorithm: str = "WCM",
                group=None, proposal_model: Optional[ImitativeModel] = None,
-               use_cuda_graphs: bool = False) -> None:
+               use_cuda_graphs: bool = False, flow_sharding: str = "scenes") -> None:
     """Args:
       models: the models owned by THIS rank (all E of them on one GPU).
       algorithm: "WCM" | "MA" | "BCM", semantics as written at rip/agent.py:121-127.
@@ -42,6 +55,9 @@ class RIPScorer:
         (rank r owns global models [r*E_local, (r+1)*E_local)).
       proposal_model: on ranks that do not own global model 0, a replica of it (only
         its flow decoder is used) so proposals can be regenerated locally.
+      flow_sharding: "scenes" | "models" (sharded ensembles only, see the module docstring);
+        "scenes" replicates the flow decoders of all E models on every rank (a collective at
+        construction) and needs no `proposal_model`.
       use_cuda_graphs: replay the ~55 launches of the encoder stage as ONE CUDA graph per set
         of input buffers (captured on first use; callers that feed the same device buffers
         every step, like `HostRIPPipeline`, hit the cache).  The returned `z` is then the
@@ -55,8 +71,14 @@ class RIPScorer:
     if group is not None:
       import torch.distributed as dist
       self._rank, self._world = dist.get_rank(group), dist.get_world_size(group)
+    assert flow_sharding in ("scenes", "models")
+    self._flow_sharding = flow_sharding if self._world > 1 else "models"
     self._proposal_model = proposal_model
-    if self._world > 1 and self._rank != 0 and proposal_model is None:
+    self._flow_ens = None       # "scenes": decoder-only ensemble over ALL E models (global order)
+    self._flow_replicas = None
+    if self._flow_sharding == "scenes":
+      self._replicate_decoders()
+    elif self._world > 1 and self._rank != 0 and proposal_model is None:
       raise ValueError("ranks other than 0 need `proposal_model` (a replica of global model 0)")
     self._ens = None
     self._ens_key = None
@@ -74,6 +96,33 @@ class RIPScorer:
       ev = torch.cuda.Event(enable_timing=True)
       ev.record()
       self.stage_events.append((name, ev))
+
+  def _replicate_decoders(self) -> None:
+    """Every rank gets a replica of the AutoregressiveFlow of each of the E models (global
+    order): the owner broadcasts the decoder's 8 parameter tensors (61 KB)."""
+    import torch.distributed as dist
+    from oatomobile_b200.networks import AutoregressiveFlow
+    e_local = len(self._models)
+    ref = self._models[0]
+    dev = next(ref.parameters()).device
+    replicas = []
+    for m in range(e_local * self._world):
+      owner, idx = divmod(m, e_local)
+      flow = AutoregressiveFlow(output_shape=ref._output_shape).to(dev)
+      if owner == self._rank:
+        flow.load_state_dict(self._models[idx]._decoder.state_dict(), strict=True)
+      for t in list(flow.parameters()) + list(flow.buffers()):
+        dist.broadcast(t.data, src=dist.get_global_rank(self._group, owner), group=self._group)
+      replicas.append(flow.eval())
+    self._flow_replicas = replicas
+    self._flow_ens = N.EnsembleHandle([f._handle() for f in replicas])
+
+  def _proposal_handle(self) -> N.ModelHandle:
+    """Decoder of global model 0 on this rank (its owner, a replica, or `proposal_model`)."""
+    if self._flow_replicas is not None:
+      return self._flow_replicas[0]._handle()
+    prop = self._models[0] if self._rank == 0 else self._proposal_model
+    return prop._decoder._handle()
 
   # ---- handles ---------------------------------------------------------------
   def _ensemble(self) -> N.EnsembleHandle:
@@ -164,7 +213,8 @@ class RIPScorer:
     return self._vis_buf
 
   def score(self, z: torch.Tensor, x: torch.Tensor, goal: Optional[torch.Tensor] = None,
-            epsilon: float = 1.0, want_s: bool = False, x_is_local: bool = False) -> Dict[str, torch.Tensor]:
+            epsilon: float = 1.0, want_s: bool = False, x_is_local: bool = False,
+            gather_details: bool = True) -> Dict[str, torch.Tensor]:
     """z [E_local,B,64], x [B,K,T,2] → plan/kstar/sbest (+ y, q, s).  With `x_is_local` (sharded
     ensembles) `x` holds only this rank's B/R scenes — the ones whose proposals it decodes."""
     ens = self._ensemble()
@@ -172,6 +222,8 @@ class RIPScorer:
     if self._world == 1:
       y, q = ops.rip_sample_score(ens, z, x, goal, epsilon, proposal_idx=0)
       self._mark("flow_end")
+    elif self._flow_sharding == "scenes" and (x_is_local or z.shape[1] % self._world == 0):
+      return self._score_by_scenes(z, x, goal, epsilon, want_s, x_is_local, gather_details)
     else:
       import torch.distributed as dist
       # (1) z_0 from the owner of model 0 (64 floats per scene).
@@ -184,9 +236,8 @@ class RIPScorer:
         # scoring): the flow stage of ranks != 0 cost 2x rank 0's at one model per rank.
         n = Bn // self._world
         lo = self._rank * n
-        prop = self._models[0] if self._rank == 0 else self._proposal_model
         x_loc = x if x_is_local else x[lo:lo + n]
-        y_part, _ = ops.flow_forward(prop._decoder._handle(), x_loc.reshape(-1, Tn, 2),
+        y_part, _ = ops.flow_forward(self._proposal_handle(), x_loc.reshape(-1, Tn, 2),
                                      z0[lo:lo + n], rows_per_z=Kn)
         y = torch.empty((Bn, Kn, Tn, 2), device=x.device, dtype=x.dtype)
         dist.all_gather_into_tensor(y, y_part.view(n, Kn, Tn, 2).contiguous(), group=self._group)
@@ -195,8 +246,7 @@ class RIPScorer:
         y, q = ops.rip_sample_score(ens, z, x, goal, epsilon, proposal_idx=0)
       else:
         # (2') identical proposals, regenerated locally from the replicated decoder.
-        y, _ = ops.flow_forward(self._proposal_model._decoder._handle(),
-                                x.reshape(-1, Tn, 2), z0, rows_per_z=Kn)
+        y, _ = ops.flow_forward(self._proposal_handle(), x.reshape(-1, Tn, 2), z0, rows_per_z=Kn)
         y = y.view_as(x)
         _, q = ops.rip_sample_score(ens, z, None, goal, epsilon, proposal_idx=-1, y=y)
       self._mark("flow_end")
@@ -249,8 +299,44 @@ class RIPScorer:
       goal_all = gbuf.view(n * R, goal.shape[1], 2)
     return vis, scal, goal_all
 
+  def _score_by_scenes(self, z, x, goal, epsilon, want_s, x_is_local, gather_details):
+    """flow_sharding="scenes": all-gather z, then the single-GPU flow stage on this rank's scenes."""
+    import torch.distributed as dist
+    R, r = self._world, self._rank
+    e_local, B = z.shape[0], z.shape[1]
+    n = B // R
+    lo = r * n
+    # the one collective between encoder and flow: every model's latents, global model order
+    z_all = torch.empty(R * e_local, B, 64, device=z.device, dtype=z.dtype)
+    dist.all_gather_into_tensor(z_all, z.contiguous(), group=self._group)
+    z_loc = z_all[:, lo:lo + n].contiguous()
+    x_loc = x if x_is_local else x[lo:lo + n]
+    goal_loc = None if goal is None else goal[lo:lo + n].contiguous()
+    y, q = ops.rip_sample_score(self._flow_ens, z_loc, x_loc.contiguous(), goal_loc, epsilon, proposal_idx=0)
+    self._mark("flow_end")
+    self._mark("aggregate_begin")
+    kstar, sbest, plan, s = ops.rip_aggregate(q, y, self._algorithm, want_s=want_s)
+    # results of all scenes on every rank (B x (T*2 + 2) floats)
+    def gather(t):
+      full = torch.empty((B,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+      dist.all_gather_into_tensor(full, t.contiguous(), group=self._group)
+      return full
+    out = dict(plan=gather(plan), kstar=gather(kstar), sbest=gather(sbest))
+    self._mark("aggregate_end")
+    if gather_details:  # the full proposal / score tensors (tests, equality checks); not on the hot path
+      out["y"] = gather(y)
+      out["q"] = gather(q.transpose(0, 1).contiguous()).transpose(0, 1).contiguous()
+      if want_s:
+        out["s"] = gather(s)
+    else:
+      out["y"], out["q"] = y, q  # this rank's scenes only
+      if want_s:
+        out["s"] = s
+    out["z_all"] = z_all
+    return out
+
   def __call__(self, x: torch.Tensor, goal: Optional[torch.Tensor] = None, epsilon: float = 1.0,
-               want_s: bool = False, local_slice: bool = False,
+               want_s: bool = False, local_slice: bool = False, gather_details: bool = True,
                **context: torch.Tensor) -> Dict[str, torch.Tensor]:
     """Full step of the metric on device-resident inputs.  `context` holds either
     `lidar` [B,C,200,200] (raw) or `visual_features` [B,C,100,100] (transformed).
@@ -265,7 +351,7 @@ class RIPScorer:
       self._mark("encode_begin")
       z = self.encode(scalars=scal, visual_features=vis)
       self._mark("encode_end")
-      out = self.score(z, x, goal, epsilon, want_s, x_is_local=True)
+      out = self.score(z, x, goal, epsilon, want_s, x_is_local=True, gather_details=gather_details)
       out["z"] = z
       return out
     if "lidar" in context:
@@ -290,7 +376,7 @@ class RIPScorer:
     self._mark("encode_begin")
     z = self.encode(**context)
     self._mark("encode_end")
-    out = self.score(z, x, goal, epsilon, want_s)
+    out = self.score(z, x, goal, epsilon, want_s, gather_details=gather_details)
     out["z"] = z
     return out
 
@@ -348,7 +434,8 @@ class HostRIPPipeline:
   def _score_slot(self, slot, epsilon):
     d = dict(self._dev[slot])
     x, goal = d.pop("x"), d.pop("goal")
-    return self._scorer(x=x, goal=goal, epsilon=epsilon, local_slice=self._sharded[slot], **d)
+    return self._scorer(x=x, goal=goal, epsilon=epsilon, local_slice=self._sharded[slot],
+                        gather_details=False, **d)
 
   def _result_rows(self, slot, lo, hi):
     """Host rows this rank reads back: with sharded inputs its own scenes only (every rank holds

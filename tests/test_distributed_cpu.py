@@ -114,7 +114,7 @@ def _worker(rank, world, port, algo, out_path):
   e_local = E // world
   mine = [_FakeModel(sds[m]) for m in range(rank * e_local, (rank + 1) * e_local)]
   group = dist.new_group(list(range(world)))
-  scorer = RIPScorer(mine, algo, group=group,
+  scorer = RIPScorer(mine, algo, group=group, flow_sharding="models",
                      proposal_model=None if rank == 0 else _FakeModel(sds[0]))
   with torch.no_grad():
     # raw grids: exercises the sharded resize + all-gather of visual features too (B=3 is not
@@ -139,6 +139,27 @@ def _worker(rank, world, port, algo, out_path):
                    is_at_traffic_light=inp["is_at_traffic_light"][sl],
                    traffic_light_state=inp["traffic_light_state"][sl])
     ok = ok and all(torch.equal(loc[k], out[k]) for k in ("q", "s", "kstar", "plan", "y", "z"))
+    # flow_sharding="scenes": z all-gathered, every rank runs the full flow stage on its scenes
+    # with replicas of all decoders (here: the fake handles of all E models), results gathered
+    from oatomobile_b200 import _native
+
+    def fake_replicas(self):
+      self._flow_replicas = [_FakeDecoder(sd) for sd in sds]
+      self._flow_ens = _native.EnsembleHandle([d._handle() for d in self._flow_replicas])
+
+    RIPScorer._replicate_decoders = fake_replicas
+    by_scene = RIPScorer(mine, algo, group=group, flow_sharding="scenes")
+    with torch.no_grad():
+      sc = by_scene(x=inp["x"], goal=inp["goal"], epsilon=1.0, want_s=True, lidar=inp["lidar"],
+                    velocity=inp["velocity"], is_at_traffic_light=inp["is_at_traffic_light"],
+                    traffic_light_state=inp["traffic_light_state"])
+      sc_loc = by_scene(x=inp["x"][sl], goal=inp["goal"][sl], epsilon=1.0, want_s=True, local_slice=True,
+                        gather_details=False, lidar=inp["lidar"][sl], velocity=inp["velocity"][sl],
+                        is_at_traffic_light=inp["is_at_traffic_light"][sl],
+                        traffic_light_state=inp["traffic_light_state"][sl])
+    ok = ok and all(torch.equal(sc[k], out[k]) for k in ("q", "s", "kstar", "plan", "y"))
+    ok = ok and all(torch.equal(sc_loc[k], out[k]) for k in ("kstar", "plan", "sbest"))
+    ok = ok and torch.equal(sc_loc["q"], out["q"][:, sl])  # details stay rank-local on the hot path
   # every rank must hold the same selection
   ks = [torch.empty_like(out["kstar"]) for _ in range(world)]
   dist.all_gather(ks, out["kstar"])
@@ -169,7 +190,7 @@ def _worker_groups(rank, world, port, out_path):
       group = pg
   sds = [synthetic_state_dict("dim", C, 800 + m) for m in range(E2)]
   inp = synthetic_inputs(2, C, K, T, seed=10 + group_id)  # each group has its own scenes
-  scorer = RIPScorer([_FakeModel(sds[grank])], "WCM", group=group,
+  scorer = RIPScorer([_FakeModel(sds[grank])], "WCM", group=group, flow_sharding="models",
                      proposal_model=None if grank == 0 else _FakeModel(sds[0]))
   with torch.no_grad():
     vis = R.transform_visual(inp["lidar"])
@@ -216,6 +237,6 @@ def test_non_zero_rank_needs_proposal_model():
     d.get_rank = lambda g=None: 1
     d.get_world_size = lambda g=None: 2
     with pytest.raises(ValueError):
-      RIPScorer([], "WCM", group=G(), proposal_model=None)
+      RIPScorer([], "WCM", group=G(), proposal_model=None, flow_sharding="models")
   finally:
     d.get_rank, d.get_world_size = orig

@@ -43,7 +43,9 @@ def _worker(rank, world, port, out_path):
   e_local = E // world
   mine = [make(m) for m in range(rank * e_local, (rank + 1) * e_local)]
   group = dist.new_group(list(range(world)))
-  sharded = RIPScorer(mine, "WCM", group=group, proposal_model=None if rank == 0 else make(0))
+  sharded = RIPScorer(mine, "WCM", group=group, proposal_model=None if rank == 0 else make(0),
+                      flow_sharding="models")
+  by_scenes = RIPScorer(mine, "WCM", group=group)  # default: flow stage sharded by scenes
   d = {k: v.to(dev) for k, v in inp.items()}
   x, goal = d.pop("x"), d.pop("goal")
   out = sharded(x=x, goal=goal, want_s=True, **d)
@@ -57,6 +59,13 @@ def _worker(rank, world, port, out_path):
   loc = sharded(x=x[sl], goal=goal[sl], want_s=True, local_slice=True,
                 **{k: v[sl] for k, v in d.items()})
   ok_local = all(torch.equal(loc[k], ref[k]) for k in ("q", "s", "kstar", "plan", "y"))
+  # the default layout: z all-gathered, each rank runs the whole flow stage on its scenes
+  sc = by_scenes(x=x, goal=goal, want_s=True, **d)
+  sc_loc = by_scenes(x=x[sl], goal=goal[sl], want_s=True, local_slice=True, gather_details=False,
+                     **{k: v[sl] for k, v in d.items()})
+  ok_scenes = (all(torch.equal(sc[k], ref[k]) for k in ("q", "s", "kstar", "plan", "y", "sbest")) and
+               all(torch.equal(sc_loc[k], ref[k]) for k in ("kstar", "plan", "sbest")) and
+               torch.equal(sc_loc["q"], ref["q"][:, sl]))
   # host pipeline with slices whose shard decision differs (B=9, chunks=2, R=2 ->
   # slice 0 has 4 scenes (sharded), slice 1 has 5 (replicated)): results == single GPU
   from oatomobile_b200.rip import HostRIPPipeline
@@ -65,12 +74,15 @@ def _worker(rank, world, port, out_path):
   d9 = {k: v.to(dev) for k, v in inp9.items()}
   x9, g9 = d9.pop("x"), d9.pop("goal")
   ref9 = single(x=x9, goal=g9, **d9)
-  res = HostRIPPipeline(sharded, dev, chunks=2)(host)
-  torch.cuda.synchronize()
   rows = list(range(rank * 2, rank * 2 + 2)) + list(range(4, 9))  # own rows of slice 0 + all of slice 1
-  ok_pipe = (torch.equal(res["kstar"][rows], ref9["kstar"].cpu()[rows]) and
-             torch.equal(res["plan"][rows], ref9["plan"].cpu()[rows]))
-  torch.save({"ok": bool(ok), "ok_local": bool(ok_local), "ok_pipe": bool(ok_pipe)}, out_path % rank)
+  ok_pipe = True
+  for scorer in (sharded, by_scenes):
+    res = HostRIPPipeline(scorer, dev, chunks=2)(host)
+    torch.cuda.synchronize()
+    ok_pipe = ok_pipe and (torch.equal(res["kstar"][rows], ref9["kstar"].cpu()[rows]) and
+                           torch.equal(res["plan"][rows], ref9["plan"].cpu()[rows]))
+  torch.save({"ok": bool(ok), "ok_local": bool(ok_local), "ok_pipe": bool(ok_pipe),
+              "ok_scenes": bool(ok_scenes)}, out_path % rank)
   dist.destroy_process_group()
 
 
@@ -84,6 +96,7 @@ def test_sharded_equals_single_gpu(tmp_path):
     assert res["ok"], "rank %d differs from the single-GPU result" % r
     assert res["ok_local"], "rank %d: rank-local feed differs from the single-GPU result" % r
     assert res["ok_pipe"], "rank %d: host pipeline (mixed shard decisions) differs" % r
+    assert res["ok_scenes"], "rank %d: scene-sharded flow stage differs from the single-GPU result" % r
 
 
 def _train_worker(rank, world, port, out_path):
