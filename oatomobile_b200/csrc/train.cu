@@ -47,12 +47,69 @@ struct BlockSize<train::CilL1Step> {
 // produce identical bits; at B = 64 the pass drops from 0.96 ms (64 threads on the whole chip)
 // to tens of microseconds.
 // ---------------------------------------------------------------------------------------------
+// gru_forward for hidden unit j (h, us in shared memory); returns h'_j, records the step
+__device__ __forceinline__ float coop_gru_forward(const train::DecParams& p, const float* us, const float* h,
+                                                   float* rec, int j) {
+  using namespace train;
+  float ar = p.bhh[j], ag = p.bhh[64 + j], an = p.bhh[128 + j], ar2 = 0.0f, ag2 = 0.0f, an2 = 0.0f;
+  const float *wr = p.whh + j * 64, *wg = p.whh + (64 + j) * 64, *wn = p.whh + (128 + j) * 64;
+#pragma unroll
+  for (int k = 0; k < 64; k += 4) {
+    const F4 a = ld4(wr + k), bb = ld4(wg + k), c = ld4(wn + k);
+    ar = fmaf(a.x, h[k], ar); ar2 = fmaf(a.y, h[k + 1], ar2);
+    ar = fmaf(a.z, h[k + 2], ar); ar2 = fmaf(a.w, h[k + 3], ar2);
+    ag = fmaf(bb.x, h[k], ag); ag2 = fmaf(bb.y, h[k + 1], ag2);
+    ag = fmaf(bb.z, h[k + 2], ag); ag2 = fmaf(bb.w, h[k + 3], ag2);
+    an = fmaf(c.x, h[k], an); an2 = fmaf(c.y, h[k + 1], an2);
+    an = fmaf(c.z, h[k + 2], an); an2 = fmaf(c.w, h[k + 3], an2);
+  }
+  ar += ar2; ag += ag2; an += an2;
+  const float u0 = us[0], u1 = us[1];
+  const float ir = fmaf(p.wih[j * 2 + 1], u1, fmaf(p.wih[j * 2], u0, p.bih[j]));
+  const float ig = fmaf(p.wih[(64 + j) * 2 + 1], u1, fmaf(p.wih[(64 + j) * 2], u0, p.bih[64 + j]));
+  const float in = fmaf(p.wih[(128 + j) * 2 + 1], u1, fmaf(p.wih[(128 + j) * 2], u0, p.bih[128 + j]));
+  const float r = sigmoidf_(ir + ar), g = sigmoidf_(ig + ag);
+  const float n = tanhf(fmaf(r, an, in));
+  const float hc = fmaf(g, h[j] - n, n);
+  rec[kRecH + j] = h[j]; rec[kRecR + j] = r; rec[kRecG + j] = g; rec[kRecN + j] = n;
+  rec[kRecHn + j] = an; rec[kRecHcur + j] = hc;
+  return hc;
+}
+
+// gru_backward: thread j turns d = dh[j] into the gate gradients of unit j (recorded, and left in
+// ghs / gis for the transposed products), then returns dh_prev[j] accumulated in the functor's
+// order: for unit u ascending: (u == j: + d_j g_j), then the three gates' W_hh[row][j] terms.
+// Contains two barriers; ghs / gis hold the step's d(W_hh h) / d(W_ih u) gradients afterwards.
+__device__ __forceinline__ float coop_gru_backward(const train::DecParams& p, float* rec, float d, float* ghs,
+                                                    float* gis, int j) {
+  using namespace train;
+  const float hp = rec[kRecH + j], r = rec[kRecR + j], g = rec[kRecG + j], n = rec[kRecN + j],
+              an = rec[kRecHn + j];
+  const float dn_pre = d * (1.0f - g) * (1.0f - n * n);
+  const float dg_pre = d * (hp - n) * g * (1.0f - g);
+  const float dr_pre = dn_pre * an * r * (1.0f - r);
+  const float dhn = dn_pre * r;
+  rec[kRecDgi + j] = dr_pre; rec[kRecDgi + 64 + j] = dg_pre; rec[kRecDgi + 128 + j] = dn_pre;
+  rec[kRecDgh + j] = dr_pre; rec[kRecDgh + 64 + j] = dg_pre; rec[kRecDgh + 128 + j] = dhn;
+  __syncthreads();  // previous readers of ghs / gis are done
+  ghs[j] = dr_pre; ghs[64 + j] = dg_pre; ghs[128 + j] = dhn;
+  gis[j] = dr_pre; gis[64 + j] = dg_pre; gis[128 + j] = dn_pre;
+  __syncthreads();
+  float acc = 0.0f;
+  for (int u = 0; u < 64; ++u) {
+    if (u == j) acc = fmaf(d, g, acc);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) acc = fmaf(ghs[q * 64 + u], p.whh[(q * 64 + u) * 64 + j], acc);
+  }
+  return acc;
+}
+
 __global__ void __launch_bounds__(64) dim_nll_coop_kernel(train::DimNllStep f) {
   using namespace train;
   const int b = blockIdx.x, j = threadIdx.x;
   const DecParams& p = f.p;
   const int T = f.T;
-  __shared__ float h[64], hn[64], a1s[32], os[4], dh[64], ghs[192], das[32], us[2];
+  __shared__ float h[64], hn[64], a1s[32], os[4], ghs[192], gis[192], das[32], us[2];
   h[j] = f.z[(int64_t)b * 64 + j];
   float* rec0 = f.scratch + (int64_t)b * T * kDecRecord;
   const float* yb = f.y + (int64_t)b * T * 2;
@@ -68,31 +125,7 @@ __global__ void __launch_bounds__(64) dim_nll_coop_kernel(train::DimNllStep f) {
       misc[6 + j] = u;
     }
     __syncthreads();
-    {  // gru_forward, unit j
-      float ar = p.bhh[j], ag = p.bhh[64 + j], an = p.bhh[128 + j], ar2 = 0.0f, ag2 = 0.0f, an2 = 0.0f;
-      const float *wr = p.whh + j * 64, *wg = p.whh + (64 + j) * 64, *wn = p.whh + (128 + j) * 64;
-#pragma unroll
-      for (int k = 0; k < 64; k += 4) {
-        const F4 a = ld4(wr + k), bb = ld4(wg + k), c = ld4(wn + k);
-        ar = fmaf(a.x, h[k], ar); ar2 = fmaf(a.y, h[k + 1], ar2);
-        ar = fmaf(a.z, h[k + 2], ar); ar2 = fmaf(a.w, h[k + 3], ar2);
-        ag = fmaf(bb.x, h[k], ag); ag2 = fmaf(bb.y, h[k + 1], ag2);
-        ag = fmaf(bb.z, h[k + 2], ag); ag2 = fmaf(bb.w, h[k + 3], ag2);
-        an = fmaf(c.x, h[k], an); an2 = fmaf(c.y, h[k + 1], an2);
-        an = fmaf(c.z, h[k + 2], an); an2 = fmaf(c.w, h[k + 3], an2);
-      }
-      ar += ar2; ag += ag2; an += an2;
-      const float u0 = us[0], u1 = us[1];
-      const float ir = fmaf(p.wih[j * 2 + 1], u1, fmaf(p.wih[j * 2], u0, p.bih[j]));
-      const float ig = fmaf(p.wih[(64 + j) * 2 + 1], u1, fmaf(p.wih[(64 + j) * 2], u0, p.bih[64 + j]));
-      const float in = fmaf(p.wih[(128 + j) * 2 + 1], u1, fmaf(p.wih[(128 + j) * 2], u0, p.bih[128 + j]));
-      const float r = sigmoidf_(ir + ar), g = sigmoidf_(ig + ag);
-      const float n = tanhf(fmaf(r, an, in));
-      const float hc = fmaf(g, h[j] - n, n);
-      rec[kRecH + j] = h[j]; rec[kRecR + j] = r; rec[kRecG + j] = g; rec[kRecN + j] = n;
-      rec[kRecHn + j] = an; rec[kRecHcur + j] = hc;
-      hn[j] = hc;
-    }
+    hn[j] = coop_gru_forward(p, us, h, rec, j);
     __syncthreads();
     if (j < 32) {  // head hidden layer
       float acc = p.b1[j], acc2 = 0.0f;
@@ -129,8 +162,7 @@ __global__ void __launch_bounds__(64) dim_nll_coop_kernel(train::DimNllStep f) {
   }
   if (j == 0) atomicAdd(f.loss, (double)row_loss);
 
-  dh[j] = 0.0f;
-  __syncthreads();
+  float dh = 0.0f;  // dh[j]: only thread j ever touches it
   for (int t = T - 1; t >= 0; --t) {
     float* rec = rec0 + t * kDecRecord;
     const float* misc = rec + kRecMisc;
@@ -144,6 +176,7 @@ __global__ void __launch_bounds__(64) dim_nll_coop_kernel(train::DimNllStep f) {
       dout[2 + d] = dsigma * (sraw > 20.0f ? 1.0f : sigmoidf_(sraw));
     }
     if (j < 4) rec[kRecDout + j] = dout[j];
+    __syncthreads();  // das of the previous step has been consumed
     if (j < 32) {
       float da = 0.0f;
 #pragma unroll
@@ -153,42 +186,85 @@ __global__ void __launch_bounds__(64) dim_nll_coop_kernel(train::DimNllStep f) {
       das[j] = da;
     }
     __syncthreads();
-    {  // dh[k] += sum_j da[j] * W1[j][k], j ascending (zero terms add nothing)
-      float acc = dh[j];
-      for (int q = 0; q < 32; ++q) {
-        const float da = das[q];
-        if (da != 0.0f) acc = fmaf(da, p.w1[q * 64 + j], acc);
+    for (int q = 0; q < 32; ++q) {  // dh[k] += sum_j da[j] * W1[j][k], j ascending (zero terms add nothing)
+      const float da = das[q];
+      if (da != 0.0f) dh = fmaf(da, p.w1[q * 64 + j], dh);
+    }
+    dh = coop_gru_backward(p, rec, dh, ghs, gis, j);  // inputs are data: du is not needed
+  }
+  f.gz[(int64_t)b * 64 + j] = dh;
+}
+
+// Same for the CIL roll-out (train_functors.h: CilL1Step): x_{t-1} feeds both the residual and the
+// GRU input, so the reverse sweep also needs du (a 192-term chain, done by thread 0 in the
+// functor's order).
+__global__ void __launch_bounds__(64) cil_l1_coop_kernel(train::CilL1Step f) {
+  using namespace train;
+  const int b = blockIdx.x, j = threadIdx.x;
+  const DecParams& p = f.p;
+  const int T = f.T;
+  __shared__ float h[64], hn[64], ghs[192], gis[192], xs[2], dxs[2];
+  h[j] = f.z[(int64_t)b * 64 + j];
+  float* rec0 = f.scratch + (int64_t)b * T * kDecRecord;
+  const float* yb = f.y + (int64_t)b * T * 2;
+  const float invB = 1.0f / (float)f.B;
+  float row_loss = 0.0f;  // thread 0 only
+  if (j < 2) xs[j] = 0.0f;
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    float* rec = rec0 + t * kDecRecord;
+    float* misc = rec + kRecMisc;
+    if (j < 2) misc[j] = xs[j];
+    hn[j] = coop_gru_forward(p, xs, h, rec, j);
+    __syncthreads();
+    if (j == 0) {
+      for (int d = 0; d < 2; ++d) {
+        float acc = p.b1[d];
+        for (int k = 0; k < 64; ++k) acc = fmaf(p.w1[d * 64 + k], hn[k], acc);
+        const float x = xs[d] + acc;
+        const float e = x - yb[t * 2 + d];
+        misc[2 + d] = e > 0.0f ? 1.0f : (e < 0.0f ? -1.0f : 0.0f);
+        row_loss += fabsf(e);
+        if (f.pred) f.pred[((int64_t)b * T + t) * 2 + d] = x;
+        xs[d] = x;
       }
-      dh[j] = acc;
+    }
+    h[j] = hn[j];
+    __syncthreads();
+  }
+  if (j == 0) atomicAdd(f.loss, (double)row_loss);
+
+  float dh = 0.0f;
+  if (j < 2) dxs[j] = 0.0f;
+  __syncthreads();
+  for (int t = T - 1; t >= 0; --t) {
+    float* rec = rec0 + t * kDecRecord;
+    const float* misc = rec + kRecMisc;
+    if (j == 0) {
+      for (int d = 0; d < 2; ++d) {
+        dxs[d] += misc[2 + d] * invB;  // x_t = x_{t-1} + W_o h_t + b_o
+        rec[kRecDout + d] = dxs[d];
+      }
     }
     __syncthreads();
-    float d_own, g_own;  // the diagonal term of dh_prev[j] is fma(d_j, g_j, .)
-    {  // gru_backward, gate gradients of unit j
-      const float hp = rec[kRecH + j], r = rec[kRecR + j], g = rec[kRecG + j], n = rec[kRecN + j],
-                  an = rec[kRecHn + j];
-      const float d = dh[j];
-      const float dn_pre = d * (1.0f - g) * (1.0f - n * n);
-      const float dg_pre = d * (hp - n) * g * (1.0f - g);
-      const float dr_pre = dn_pre * an * r * (1.0f - r);
-      const float dhn = dn_pre * r;
-      rec[kRecDgi + j] = dr_pre; rec[kRecDgi + 64 + j] = dg_pre; rec[kRecDgi + 128 + j] = dn_pre;
-      rec[kRecDgh + j] = dr_pre; rec[kRecDgh + 64 + j] = dg_pre; rec[kRecDgh + 128 + j] = dhn;
-      ghs[j] = dr_pre; ghs[64 + j] = dg_pre; ghs[128 + j] = dhn;
-      d_own = d; g_own = g;
-    }
-    __syncthreads();
-    {  // dh_prev[k]: for unit u ascending: (u == k: + d_k g_k), then the three gates' W_hh rows
-      float acc = 0.0f;
-      for (int u = 0; u < 64; ++u) {
-        if (u == j) acc = fmaf(d_own, g_own, acc);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) acc = fmaf(ghs[q * 64 + u], p.whh[(q * 64 + u) * 64 + j], acc);
+    for (int d = 0; d < 2; ++d) dh = fmaf(dxs[d], p.w1[d * 64 + j], dh);
+    dh = coop_gru_backward(p, rec, dh, ghs, gis, j);
+    if (j == 0) {  // du: the functor's chain over unit u ascending, gates r|z|n inside
+      float du0 = 0.0f, du1 = 0.0f;
+      for (int u = 0; u < 64; ++u) {
+        for (int q = 0; q < 3; ++q) {
+          const int row = q * 64 + u;
+          du0 = fmaf(gis[row], p.wih[row * 2], du0);
+          du1 = fmaf(gis[row], p.wih[row * 2 + 1], du1);
+        }
       }
-      dh[j] = acc;  // dh[j] is only ever read by thread j in this sweep (d_own was taken above)
+      dxs[0] += du0;  // x_{t-1} also feeds the GRU input of step t
+      dxs[1] += du1;
     }
     __syncthreads();
   }
-  f.gz[(int64_t)b * 64 + j] = dh[j];
+  f.gz[(int64_t)b * 64 + j] = dh;
 }
 
 // W [N][K] (reference layout, changes every step) -> W^T [K][N] for the tiled GEMM's B operand
@@ -285,6 +361,15 @@ struct CudaBackend {
     dim_nll_coop_kernel<<<(unsigned)n, 64, 0, stream>>>(f);
     g_launch_count++;
     if (g_profile_on) profile_mark("DimNllStep", stream);
+    note(cudaGetLastError());
+  }
+  void run(int64_t n, const train::CilL1Step& f) {
+    static const int coop = []() { const char* e = getenv("OAT_TRAIN_COOP"); return e ? atoi(e) : 1; }();
+    if (n <= 0) return;
+    if (!coop) { run<train::CilL1Step>(n, f); return; }
+    cil_l1_coop_kernel<<<(unsigned)n, 64, 0, stream>>>(f);
+    g_launch_count++;
+    if (g_profile_on) profile_mark("CilL1Step", stream);
     note(cudaGetLastError());
   }
   template <class F>
