@@ -17,13 +17,22 @@
 // round-robin over `C` accumulators by k-block (C = ceil(K/512)); the epilogue adds
 // the partial tiles in round-to-nearest fp32.  Error -> (K/8)*6e-8/C <= 4e-6.
 //
-// Round 2 (measured with tools/tc_trace.py, profiles/r2_gemm_pipeline_trace.txt): at these
-// tile widths (N <= 160) a tcgen05.mma is bound by the shared-memory reads of its operands
-// (4 KB of A + 32*N B of B per K=8 slice, ~57 + 0.2*N cycles measured), not by the tensor
-// pipe, and the issuing thread behind `if (lane == 0)` paid an ELECT/BRA serialisation loop
-// per instruction.  Hence: (a) the issuer warp runs converged and elects one lane with
-// elect.sync; (b) the three products take TWO instructions per K slice: a_hi meets the
-// stacked operand [W_hi ; W_lo] (adjacent tiles of a stage, N = 2*BN) once, a_lo meets W_hi.
+// Round 2 (measured with tools/tc_trace.py, profiles/r2_gemm_pipeline_trace.txt):
+//  * behind `if (lane == 0)` ptxas wrapped EVERY tcgen05.mma in an ELECT / BRA.U.ANY serialisation
+//    loop; the issuer warp now runs converged and elects one lane with elect.sync;
+//  * the k-block period of the main loop equals the shared-memory traffic of a stage (TMA writes
+//    + split read/writes + the MMAs' operand reads: 4 KB of A and 32*N B of W per K=8 slice)
+//    divided by 128 B/clk for BN <= 128, and the tensor-pipe time (12 MMAs x 81 cycles) at
+//    BN = 160 -> tiles as wide as TMEM allows: C = ceil(K/512) instead of ceil(K/200);
+//  * per-layer tile policy (tc_pw_gemm() below): deep K (project layers, K >= 192) store straight
+//    from registers (no staging barriers, 16-column granules); shallow K (expand layers, a few
+//    k-blocks per tile, store-bound) keep the swizzled staging + TMA store and take BN <= 128 so
+//    that TWO accumulator groups fit TMEM and the epilogue of tile i overlaps tile i+1;
+//  * evaluated and left OFF (environment switches, each covered by tests/test_gpu_tc_gemm.py):
+//    OAT_TC_STACK_K (3xTF32 in two MMAs: a_hi x stacked [W_hi ; W_lo] with N = 2*BN, + a_lo x W_hi),
+//    OAT_TC_TS (A operand in tensor memory, written by the splitters with tcgen05.st),
+//    OAT_TC_WSPLIT (unsplit weights streamed from L2 and split in shared memory),
+//    and the depthwise 3x3 epilogue of TcGemmProblem::dw_out (fusion bit 5).
 //
 // Structure (one persistent CTA per SM, 448 threads, warp-specialised):
 //   (warp numbers for the default of 4 splitter warps, -DOAT_TC_SPLIT_WARPS=n shifts the last two)
@@ -33,16 +42,16 @@
 //            buffer) in shared memory — the split is element-wise, so it is
 //            layout-agnostic w.r.t. the TMA swizzle; fence.proxy.async hands the
 //            tiles to the tensor core;
-//   warp 13  MMA issuer: one elected thread issues 3 tcgen05.mma.kind::tf32 per
-//            8-wide k-slice into a TMEM accumulator (128 lanes x BN columns fp32),
-//            tcgen05.commit releases smem stages / publishes the accumulator;
+//   warp 13  MMA issuer: the warp walks the loop converged, one elect.sync lane issues 3
+//            tcgen05.mma.kind::tf32 per 8-wide k-slice into TMEM accumulators (128 lanes x BN
+//            columns fp32), tcgen05.commit releases smem stages / publishes the accumulator;
 //   warps0-7 epilogue (two groups of 4, alternating 32-column slabs): tcgen05.ld 32x32b
 //            (one output row per thread), RN sum of the
-//            partial accumulators, folded-BN bias, ReLU6, residual; 32-column slabs
+//            partial accumulators, folded-BN bias, ReLU6, residual; shallow K: 32-column slabs
 //            are staged in 128B-swizzled shared memory and written with TMA stores
-//            (cp.async.bulk.tensor, double-buffered), which also clip the M/N tails.
-//            When TMEM allows, two accumulator groups overlap the epilogue of tile i
-//            with the main loop of tile i+1.
+//            (cp.async.bulk.tensor, double-buffered), which also clip the M/N tails; deep K:
+//            float4 stores straight from registers.  When TMEM allows, two accumulator groups
+//            overlap the epilogue of tile i with the main loop of tile i+1.
 #include <cuda.h>
 
 #include <cstdlib>
