@@ -38,22 +38,22 @@ def _bool(v):
 def parse_flags(argv: Sequence[str]) -> argparse.Namespace:
   """The reference's absl flags (dim/train.py:38-82; names, defaults and meaning kept)."""
   p = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-  p.add_argument("--dataset_dir", required=True, help="The full path to the processed dataset.")
+  p.add_argument("--dataset_dir", required=True, help="Directory of the processed dataset (with `train/` and `val/` sub-directories of .npz samples).")
   p.add_argument("--output_dir", required=True,
-                 help="The full path to the output directory (for logs, ckpts).")
+                 help="Where `logs/` and `ckpts/` are written.")
   p.add_argument("--batch_size", type=int, default=512,
-                 help="The batch size used for training the neural network.")
+                 help="Samples per optimiser step (split over the ranks under torchrun).")
   p.add_argument("--num_epochs", type=int, required=True,
-                 help="The number of training epochs for the neural network.")
+                 help="Passes over the training set.")
   p.add_argument("--save_model_frequency", type=int, default=4,
-                 help="The number epochs between saves of the model.")
-  p.add_argument("--learning_rate", type=float, default=1e-3, help="The ADAM learning rate.")
+                 help="A checkpoint is written every this many epochs.")
+  p.add_argument("--learning_rate", type=float, default=1e-3, help="Adam step size.")
   p.add_argument("--num_timesteps_to_keep", type=int, default=4,
-                 help="The numbers of time-steps to keep from the target, with downsampling.")
+                 help="T: waypoints kept from the 80-frame future by strided down-sampling.")
   p.add_argument("--weight_decay", type=float, default=0.0,
-                 help="The L2 penalty (regularization) coefficient.")
+                 help="Adam weight decay (L2).")
   p.add_argument("--clip_gradients", nargs="?", const=True, default=False, type=_bool,
-                 help="If True it clips the gradients norm to 1.0.")
+                 help="Clip the global gradient norm to 1.0 before the update.")
   # extensions
   p.add_argument("--model", choices=("dim", "cil"), default="dim",
                  help="dim: ImitativeModel (dim/train.py); cil: BehaviouralModel (cil/train.py).")
