@@ -109,7 +109,9 @@ def main(argv=None) -> int:
 
   modalities = ("lidar", "is_at_traffic_light", "traffic_light_state", "player_future", "velocity")
   with_mode = flags.model == "cil"  # cil/train.py:137-149 asks the loader for the command label
-  train_files = sorted(glob.glob(os.path.join(flags.dataset_dir, "train", "*.npz")))[rank::world]
+  all_train = sorted(glob.glob(os.path.join(flags.dataset_dir, "train", "*.npz")))
+  # equal shards: every rank must take the same number of optimiser steps (one all-reduce each)
+  train_files = all_train[rank::world][:len(all_train) // world]
   val_files = sorted(glob.glob(os.path.join(flags.dataset_dir, "val", "*.npz")))
   if not train_files:
     raise SystemExit("no training samples under %s" % os.path.join(flags.dataset_dir, "train"))
