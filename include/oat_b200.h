@@ -69,7 +69,11 @@ OAT_API int oat_model_in_channels(const OatModel* model);
 
 /* Groups E models that live on this GPU (RIPAgent.__init__, rip/agent.py:49-50).
  * Owns the activation workspace, grown on demand by `oat_ensemble_reserve`
- * (called implicitly by oat_encode). */
+ * (called implicitly by oat_encode).  All models share kind, device and in_channels.
+ * An ensemble of OAT_KIND_FLOW models holds decoders only (the replicas a rank keeps of
+ * every model's AutoregressiveFlow when the flow stage is sharded by scenes): usable with
+ * oat_rip_sample_score, rejected by oat_encode / oat_encode_features.  With
+ * OAT_KIND_ENCODER models only oat_encode_features applies.                          */
 OAT_API int oat_ensemble_create(OatModel* const* models, int32_t num_models, OatEnsemble** out);
 OAT_API int oat_ensemble_destroy(OatEnsemble* ens);
 OAT_API int oat_ensemble_reserve(OatEnsemble* ens, int32_t batch);
