@@ -42,3 +42,23 @@ def test_training_reference_arm_line():
   line = json.loads(out.splitlines()[-1])
   assert line["impl"] == "reference" and "DIM training samples/sec" in line["metric"]
   assert line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+
+
+def test_algorithmic_flops_match_the_survey():
+  """bench.py's layer table reproduces SURVEY.md §6 / §8(d): 149.7 MFLOP per image at C=2 (pointwise
+  137.3, depthwise 9.3, stem 2.9, fc 0.3) and 152.6 at C=4; the flow figure is 29 696 flop per row-step."""
+  sys.path.insert(0, ROOT)
+  import bench
+  for C, want in ((2, 149.7), (4, 152.6)):
+    L = bench.encoder_layers(C)
+    by = {}
+    for l in L:
+      by[l[0]] = by.get(l[0], 0.0) + bench.layer_flops(l) / 1e6
+    total = sum(by.values())
+    assert abs(total - want) < 0.15, (C, total, by)
+    assert abs(by["expand"] + by["project"] + by["last"] - 137.3) < 0.2
+    assert abs(by["dw"] - 9.3) < 0.1 and abs(by["fc"] - 0.33) < 0.01
+  assert bench.FLOW_FLOP_PER_ROW_STEP == 2 * (64 * 192 + 2 * 192 + 64 * 32 + 32 * 4)
+  # every family's work is defined and the GEMM family is the 31 launches DESIGN §5 names
+  w = bench.rip_family_work(bench.RIP_WORKLOADS["rip"], 4, 256, 131072, 3 * 131072, 30)
+  assert abs(w["tc_pw_gemm"][0] / 1e9 - 121.5) < 0.3 and w["flow_score"][0] == 3 * 131072 * 10 * 29696
