@@ -99,3 +99,26 @@ def test_flow_round_trip_property():
     xr, lp, lad_i = R.flow_inverse(sd, y, z)
   assert (xr - x).abs().max().item() < 2e-5
   assert_close(lad_f, lad_i, 1e-5, "forward/inverse logabsdet")
+
+
+def test_cfg1_imitative_forward_b4_c4_matches_reference():
+  """BASELINE.json configs[0] (the reference's own CPU-runnable case): `ImitativeModel.forward` on a
+  batch of 4 synthetic 200x200x4 grids, 10 Adam steps — the restatement against the real reference's
+  output (tests/golden/make_golden_cfg1.py)."""
+  import os
+  from tests.helpers import GOLDEN_DIR
+  g = dict(np.load(os.path.join(GOLDEN_DIR, "cfg1_forward_B4_C4.npz")))
+  T, C, B = 4, 4, 4
+  inp = synthetic_inputs(B, C, 1, T, seed=61)
+  sd = synthetic_state_dict("dim", C, 610)
+  with torch.no_grad():
+    vis = R.transform_visual(inp["lidar"])
+    z = R.imitative_params(sd, vis, inp["velocity"], inp["is_at_traffic_light"], inp["traffic_light_state"])
+  assert_close(z, g["z"], CPU_TOL, "cfg1 z")
+  ctx = dict(visual_features=vis, velocity=inp["velocity"], is_at_traffic_light=inp["is_at_traffic_light"],
+             traffic_light_state=inp["traffic_light_state"])
+  x0 = torch.from_numpy(g["x0"]).repeat(B, 1, 1)
+  y = R.imitative_forward(sd, x0, 10, goal=inp["goal"], lr=1e-1, epsilon=1.0, **ctx)
+  assert_close(y, g["plan_goal"], 1e-4, "cfg1 ImitativeModel.forward (goal)")
+  y = R.imitative_forward(sd, x0, 10, goal=None, lr=1e-1, epsilon=1.0, **ctx)
+  assert_close(y, g["plan_nogoal"], 1e-4, "cfg1 ImitativeModel.forward (no goal)")
