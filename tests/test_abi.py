@@ -128,3 +128,19 @@ def test_trainer_rejects_cpu_models():
   from oatomobile_b200.train import Trainer
   with pytest.raises(NativeLibraryError):
     Trainer(ob.ImitativeModel(output_shape=(4, 2)))
+
+
+def test_reference_citations_resolve():
+  """Every `file.py:LINE` citation of the reference in our docs, headers and sources names an
+  existing reference file with that many lines (tools/check_citations.py).  Needs the reference
+  checkout, so it only runs in the build container."""
+  import importlib.util
+  spec = importlib.util.spec_from_file_location(
+      "check_citations", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "check_citations.py"))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  if not os.path.isdir(mod.REF):
+    pytest.skip("reference checkout not present")
+  total, bad = mod.scan()
+  assert total > 100
+  assert not bad, "\n".join(bad)

@@ -206,6 +206,57 @@ def _worker_groups(rank, world, port, out_path):
   dist.destroy_process_group()
 
 
+def _worker_scenes4(rank, world, port, out_path):
+  """bench.py's default layout at N = 4 = E: one encoder per rank, rank-local feed of B/4 scenes,
+  `flow_sharding="scenes"` (z all-gathered, every rank decodes its own scenes with replicas of all
+  four decoders), the small per-scene results all-gathered — for all three aggregations."""
+  sys.path.insert(0, ROOT)
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  torch.set_num_threads(1)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  _install_cpu_ops()
+  from oracle import restatement as R
+  from oatomobile_b200 import _native
+  from oatomobile_b200.rip import RIPScorer
+  from oatomobile_b200.synthetic import synthetic_inputs, synthetic_state_dict
+  sds = [synthetic_state_dict("dim", C, 900 + m) for m in range(world)]
+  Bs = 2 * world
+  inp = synthetic_inputs(Bs, C, K, T, seed=21)
+  group = dist.new_group(list(range(world)))
+
+  def fake_replicas(self):
+    self._flow_replicas = [_FakeDecoder(sd) for sd in sds]
+    self._flow_ens = _native.EnsembleHandle([d._handle() for d in self._flow_replicas])
+
+  RIPScorer._replicate_decoders = fake_replicas
+  sl = slice(rank * 2, rank * 2 + 2)
+  ok = True
+  for algo in ("WCM", "MA", "BCM"):
+    scorer = RIPScorer([_FakeModel(sds[rank])], algo, group=group)  # default sharding = scenes
+    with torch.no_grad():
+      out = scorer(x=inp["x"][sl], goal=inp["goal"][sl], epsilon=1.0, want_s=True, local_slice=True,
+                   gather_details=False, lidar=inp["lidar"][sl], velocity=inp["velocity"][sl],
+                   is_at_traffic_light=inp["is_at_traffic_light"][sl],
+                   traffic_light_state=inp["traffic_light_state"][sl])
+      ref = R.rip_score_from_inputs(sds, inp["lidar"], inp["velocity"], inp["is_at_traffic_light"],
+                                    inp["traffic_light_state"], inp["x"], inp["goal"], 1.0, algo)
+    ok = ok and torch.equal(out["kstar"].long(), ref["kstar"]) and torch.equal(out["plan"], ref["plan"])
+    ok = ok and torch.equal(out["q"], ref["q"][:, sl])
+    ok = ok and tuple(out["plan"].shape) == (Bs, T, 2)
+  t = torch.tensor([1.0 if ok else 0.0])
+  dist.all_reduce(t, op=dist.ReduceOp.MIN)
+  torch.save({"ok": bool(t.item() == 1.0)}, out_path % rank)
+  dist.destroy_process_group()
+
+
+def test_scene_sharded_flow_world4_matches_single_process(tmp_path):
+  world = 4
+  out_path = str(tmp_path / "rank%d.pt")
+  mp.spawn(_worker_scenes4, args=(world, _free_port(), out_path), nprocs=world, join=True)
+  assert all(torch.load(out_path % r)["ok"] for r in range(world))
+
+
 def test_two_replica_groups_world4(tmp_path):
   world = 4
   out_path = str(tmp_path / "rank%d.pt")
