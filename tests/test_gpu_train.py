@@ -91,7 +91,7 @@ def test_cuda_and_host_execution_of_the_kernel_bodies_agree():
   emu = EmuTrainer(sd, "dim")
   loss_e, z_e = emu.forward_backward(visual, scalars, target)
   assert abs(loss.item() - loss_e.item()) < 2e-6 * abs(loss_e.item())
-  assert_close(z, z_e, tol=1e-5, what="z")
+  assert_close(z, z_e, tol=1e-5, what="train-mode forward z")
   same_branch = all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
                     for a, b in zip(branch_of(trainer, cfg["B"]).values(), emu.branch(cfg["B"]).values()))
   errs = grad_errors({k: p.grad for k, p in model.named_parameters()},
