@@ -11,10 +11,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 # End point after 10-20 Adam steps: Adam normalises the gradient (step = lr * m / sqrt(v)), so a
 # 1e-6 rounding difference in a near-zero gradient component moves x by a visible fraction of lr;
-# the reference's own CPU run differs from the CPU restatement by up to 1e-4 on these goldens.
-# The end point therefore keeps a 1e-3 bar, and the PER-STEP quantities (loss of every step, the
-# first-step gradient through its Adam update) are held to the north-star 1e-4 in
-# `test_planner_per_step_quantities`.  Achieved errors: gpurun_out/parity_achieved.json.
+# round 1 therefore held the end point to 1e-3.  Measured on B200 the end points stay within 3.2e-5
+# of the reference's (profiles/r2_parity_achieved.json), so since round 2 the end point is held to
+# the north-star 1e-4 as well, next to the PER-STEP quantities (loss of every step, the first-step
+# gradient through its Adam update) in `test_planner_per_step_quantities`.
 PLAN_TOL = 1e-4
 STEP_TOL = 1e-4
 
