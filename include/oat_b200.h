@@ -228,7 +228,9 @@ typedef struct OatTrainTensor {
 
 typedef struct OatTrainer OatTrainer;
 
-/* Binds the trainer to the caller-owned parameter / gradient storage of one
+/* Replaces the model + optimiser set-up of the train scripts
+ * (oatomobile/baselines/torch/dim/train.py:114-119, cil/train.py:112-118).
+ * Binds the trainer to the caller-owned parameter / gradient storage of one
  * `ImitativeModel` (kind OAT_KIND_DIM) or `BehaviouralModel` (OAT_KIND_CIL).  If all
  * gradients live in one flat buffer pass it as (grad_flat, grad_flat_floats) so it is
  * cleared with one memset per step; otherwise pass NULL/0.                       */
@@ -272,7 +274,7 @@ OAT_API int oat_adam_step(float* param, const float* grad, float* exp_avg, float
                   void* stream);
 
 /* Number of kernel launches issued by this library since load (bench.py's
- * `gpu_launches`). */
+ * `gpu_launches`; no reference counterpart). */
 OAT_API int64_t oat_launch_count(void);
 
 /* Per-kernel-family device timing for bench.py's `roofline` (no reference counterpart: the
