@@ -45,7 +45,11 @@ def interpolate_plan(plan: np.ndarray) -> np.ndarray:
   40-frame horizon, plus a zero z column → float64 [N,3]."""
   player_future_length = 40
   increments = player_future_length // plan.shape[0]
-  time_index = np.arange(0, player_future_length, increments)[:plan.shape[0]]
+  time_index = np.arange(0, player_future_length, increments)
+  if time_index.shape[0] != plan.shape[0]:
+    # the reference hands both to scipy's interp1d, which rejects them (T must divide 40)
+    raise ValueError("x and y arrays must be equal in length along interpolation axis "
+                     "(%d time steps for a plan of %d waypoints)" % (time_index.shape[0], plan.shape[0]))
   query = np.arange(0, time_index[-1])
   xy = np.stack([np.interp(query, time_index, plan[:, d].astype(np.float64)) for d in range(2)],
                 axis=-1)

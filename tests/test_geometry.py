@@ -4,6 +4,7 @@ restatement in oracle/euler.py, known answers and the round trip."""
 import os
 
 import numpy as np
+import pytest
 
 from oatomobile_b200 import geometry as G
 
@@ -61,3 +62,34 @@ def test_euler_restatement_conventions():
   rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
   np.testing.assert_allclose(euler2mat(a, b, c), rz @ ry @ rx, atol=1e-15)
   np.testing.assert_allclose(euler2mat(c, b, a, "rzyx"), rz @ ry @ rx, atol=1e-15)
+
+
+@pytest.mark.parametrize("T", [2, 4, 5, 8, 10, 20, 40])
+def test_interpolate_plan_equals_scipy_interp1d(T):
+  """rip/agent.py:141-151 interpolates with `scipy.interpolate.interp1d(x=time_index, y=plan,
+  axis=0)`; the product and the oracle use np.interp per column — same piecewise-linear values."""
+  import scipy.interpolate
+  from oatomobile_b200.agents import interpolate_plan
+  from oracle import restatement as R
+  rng = np.random.RandomState(T)
+  plan = rng.randn(T, 2).astype(np.float32) * 10
+  time_index = list(range(0, 40, 40 // T))
+  xy = scipy.interpolate.interp1d(x=time_index, y=plan, axis=0)(np.arange(0, time_index[-1]))
+  want = np.c_[xy, np.zeros((xy.shape[0], 1))]
+  for fn in (interpolate_plan, R.interpolate_plan):
+    got = fn(plan)
+    assert got.shape == want.shape and got.dtype == np.float64
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("T", [3, 6, 7, 9])
+def test_interpolate_plan_rejects_what_the_reference_rejects(T):
+  """For T that does not divide 40 the reference's time index has more entries than the plan and
+  interp1d raises ValueError; so does the product."""
+  import scipy.interpolate
+  from oatomobile_b200.agents import interpolate_plan
+  plan = np.zeros((T, 2), np.float32)
+  with pytest.raises(ValueError):
+    scipy.interpolate.interp1d(x=list(range(0, 40, 40 // T)), y=plan, axis=0)
+  with pytest.raises(ValueError):
+    interpolate_plan(plan)
